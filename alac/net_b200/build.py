@@ -1,0 +1,65 @@
+"""Builds libalacgpu.so (CUDA kernels + C ABI) and libalacnet_host.so (C++ host
+mirror of AlacContext / QtMovieT / ALACFileReader) in-tree for sm_100a."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+LIB_GPU = os.path.join(HERE, "libalacgpu.so")
+LIB_HOST = os.path.join(HERE, "libalacnet_host.so")
+
+CU_SOURCES = ["k0_index.cu", "k1_entropy.cu", "k2_lpc.cu", "k3_stereo.cu", "runtime.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--shared", "-cudart", "static",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_gpu(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(ROOT, "include", "alacgpu.h"))
+    if force or _newer(LIB_GPU, deps):
+        cmd = ["nvcc", *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_GPU, *srcs]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+    return LIB_GPU
+
+
+def build_host(force: bool = False) -> str:
+    if not os.path.isdir(HOST):
+        return ""
+    srcs = [os.path.join(HOST, s) for s in sorted(os.listdir(HOST)) if s.endswith(".cpp")]
+    if not srcs:
+        return ""
+    deps = srcs + [os.path.join(HOST, h) for h in os.listdir(HOST) if h.endswith((".h", ".hpp"))]
+    deps.append(os.path.join(ROOT, "include", "alacgpu.h"))
+    if force or _newer(LIB_HOST, deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"),
+               "-o", LIB_HOST, *srcs, "-ldl", "-lpthread"]
+        subprocess.check_call(cmd)
+    return LIB_HOST
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_gpu(force, verbose)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB_GPU)
