@@ -98,6 +98,7 @@ struct alacgpu_ctx {
     alacgpu_opts opts{};
     bool prepared = false;
     uint64_t total_pcm = 0;
+    uint64_t compressed_bytes = 0;
     alacgpu_timing timing{};
     std::string err;
     // read_frame support (host mirrors, filled lazily)
@@ -321,10 +322,8 @@ int32_t alacgpu_plan_partition(const uint32_t *frame_sizes, uint64_t n_frames, i
 }
 
 // ---------------------------------------------------------------------------
-int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
+static int32_t prepare_impl(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes, const bool restage)
 {
-    if (!ctx) return ALACGPU_ERR_INVALID_ARG;
-    if (ctx->prepared) { if (total_pcm_bytes) *total_pcm_bytes = ctx->total_pcm; return ALACGPU_OK; }
     const double t_begin = now_ms();
     const uint64_t n_frames = ctx->sizes.size();
     const uint32_t n_tracks = (uint32_t)ctx->tracks.size();
@@ -351,6 +350,23 @@ int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
         d.decoded = false;
         const uint64_t n_local = d.f_hi - d.f_lo;
         CU(cudaSetDevice(d.id));
+        if (!restage) {
+            // index only: the arena, FrameRef[] and TrackCfg[] staged earlier are still resident
+            cudaEvent_t e0 = get_event(d, 0), e1 = get_event(d, 1), e2 = get_event(d, 2);
+            CU(cudaEventRecord(e0, d.st));
+            CU(cudaMemsetAsync(d.scalars.p, 0, 4 * sizeof(uint64_t), d.st));
+            CU(cudaEventRecord(e1, d.st));
+            K0Args ka{};
+            ka.arena = d.arena.p; ka.refs = d.refs.p; ka.cfgs = d.cfgs.p; ka.n_frames = n_local; ka.n_tracks = n_tracks;
+            ka.track_first_frame = d.track_first.p; ka.desc = d.desc.p; ka.coefs = d.coefs.p; ka.out_len = d.out_len.p;
+            ka.block_sums = d.block_sums.p; ka.grand_total = d.scalars.p; ka.frame_off = d.frame_off.p;
+            ka.track_start = d.track_start.p; ka.max_samples = reinterpret_cast<uint32_t *>(d.scalars.p + 1);
+            if (n_local) CU(launch_k0(ka, d.st, &ctx->timing.kernel_launches));
+            CU(cudaEventRecord(e2, d.st));
+            CU(cudaMemcpyAsync(d.h_track_start.data(), d.track_start.p, (n_tracks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
+            CU(cudaMemcpyAsync(sg.sc, d.scalars.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
+            continue;
+        }
         sg.refs.resize(n_local);
         sg.cfgs.resize(std::max<uint32_t>(n_tracks, 1));
         sg.tfirst.resize(std::max<uint32_t>(n_tracks, 1));
@@ -485,7 +501,8 @@ int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
             d.pcm_lo = d.pcm_hi = d.pcm_first = 0;
         }
     }
-    ctx->timing.compressed_bytes = compressed;
+    if (restage) ctx->compressed_bytes = compressed;
+    ctx->timing.compressed_bytes = ctx->compressed_bytes;
     ctx->timing.pcm_bytes = dev_base[n_dev];
     ctx->timing.samples = samples;
     ctx->timing.total_ms = (float)(now_ms() - t_begin);
@@ -494,6 +511,20 @@ int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
     ctx->win_lo = ctx->win_hi = 0;
     if (total_pcm_bytes) *total_pcm_bytes = ctx->total_pcm;
     return ALACGPU_OK;
+}
+
+int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
+{
+    if (!ctx) return ALACGPU_ERR_INVALID_ARG;
+    if (ctx->prepared) { if (total_pcm_bytes) *total_pcm_bytes = ctx->total_pcm; return ALACGPU_OK; }
+    return prepare_impl(ctx, total_pcm_bytes, true);
+}
+
+int32_t alacgpu_reindex(alacgpu_ctx *ctx)
+{
+    if (!ctx) return ALACGPU_ERR_INVALID_ARG;
+    if (!ctx->prepared) return prepare_impl(ctx, nullptr, true);
+    return prepare_impl(ctx, nullptr, false);
 }
 
 // ---------------------------------------------------------------------------

@@ -121,6 +121,9 @@ class BatchDecoder:
         self.total_pcm = total.value
         return total.value
 
+    def reindex(self):
+        self._check(self._L.alacgpu_reindex(self._h), "alacgpu_reindex")
+
     def track_count(self) -> int:
         n = C.c_int32(0)
         self._check(self._L.alacgpu_track_count(self._h, C.byref(n)), "alacgpu_track_count")

@@ -166,6 +166,11 @@ ALACGPU_API int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx);
  * buffer decode_all needs (offsets included). */
 ALACGPU_API int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes);
 
+/* Re-run only the device side of alacgpu_prepare (header pre-pass + offset
+ * scan) over the bytes already resident in HBM; no host->device copy.  Used to
+ * time the whole kernel path with resident inputs. */
+ALACGPU_API int32_t alacgpu_reindex(alacgpu_ctx *ctx);
+
 /* Decode every frame of every track.  pcm_dst: caller-owned HOST buffer of
  * `cap` bytes, or NULL to leave the PCM device-resident (see
  * alacgpu_device_pcm).  track_pcm_off / track_pcm_len (n_tracks entries each,
