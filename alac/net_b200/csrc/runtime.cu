@@ -23,7 +23,9 @@ using namespace alacgpu;
 namespace {
 
 constexpr uint64_t kTrackAlign = 256;     // PCM start alignment of each track in the global layout
-constexpr uint64_t kArenaTail = 256;      // zero padding after the last staged byte
+// zero padding after the last staged byte: a lane whose frame is truncated keeps reading
+// (at most 2 channels x 16384 symbols x 59 bits) until K1 flags the overrun at the end
+constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kDefaultChunkFrames = 32768;
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 
