@@ -185,11 +185,7 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
         int32_t h = cfg.rice_initial_history;                                         // :216
         uint32_t sign_mod = 0;
         uint32_t zrun = 0;
-        int k;
-        {
-            const int t = 31 - kmod - __clz((h >> 9) + 3);                            // :221
-            k = t < 0 ? t + kmod : kmod;                                              // :222
-        }
+        int k = min(31 - __clz((h >> 9) + 3), kmod);                                  // :221-222
         for (int i = 0; i < n; i++) {
             if ((i & (kPeriod - 1)) == 0) {          // warp-uniform: lanes are in lock step on i
                 br.top_up();
@@ -229,8 +225,7 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
                     h = 0;                                                            // :248
                 }
             }
-            const int t = 31 - kmod - __clz((h >> 9) + 3);                            // :221
-            k = t < 0 ? t + kmod : kmod;                                              // :222
+            k = min(31 - __clz((h >> 9) + 3), kmod);                                  // :221-222
             out[(uint32_t)i * kTile] = val;
         }
     }

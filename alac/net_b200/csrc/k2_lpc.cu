@@ -55,13 +55,16 @@ __device__ __forceinline__ void lpc_tap(int32_t &c, int32_t &E, uint32_t &acc, c
         : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "r"(negm));
 }
 
+constexpr int kK2Threads = 128;
+
 // All 32 lanes run this; `active` gates memory traffic only.
 //   p      : lane's column of the plane (sample i at p[i * 32])
 //   n      : samples of this lane's stream (0 if inactive), nmax: warp maximum
 //   ord    : 1..30 general, 31 delta mode (AlacFile.cs:268-282); inactive lanes pass 31
 template <int M>
 __device__ __noinline__ void lpc_warp(int32_t *p, const int n, const int nmax, const int rss, const int ord,
-                                      const int q, const int16_t *__restrict__ coef16, const bool active)
+                                      const int q, const int16_t *__restrict__ coef16, const bool active,
+                                      int32_t *hist /* this thread's column of a [32][blockDim] shared ring */)
 {
     const bool delta = ord == 31;
     const int ordm = delta ? 0 : ord;              // taps this lane really has
@@ -87,14 +90,18 @@ __device__ __noinline__ void lpc_warp(int32_t *p, const int n, const int nmax, c
     const int sh = (32 - rss) & 31;
 
     H[0] = active ? p[0] : 0;                                       // first sample always copies (:259-260)
+    hist[0] = H[0];
+    // residuals are fetched two samples ahead (HBM latency ~ one sample's worth of taps)
     int32_t e_next = (active && n > 1) ? p[kTile] : 0;
+    int32_t e_next2 = (active && n > 2) ? p[2 * kTile] : 0;
     for (int i = 1; i < nmax; i++) {
         const bool live = active && i < n;
         const int32_t e = e_next;
-        if (active && i + 1 < n) e_next = p[(uint32_t)(i + 1) * kTile];
-        // base of the NEXT sample, o[i - ord]; already stored (ord >= 1)
-        int32_t nb = 0;
-        if (live && !delta && i >= ord) nb = p[(uint32_t)(i - ord) * kTile];
+        e_next = e_next2;
+        if (active && i + 2 < n) e_next2 = p[(uint32_t)(i + 2) * kTile];
+        // base of the NEXT sample, o[i - ord] (ord >= 1): from the lane's ring of its last 32
+        // outputs in shared memory ([slot][thread]: bank == lane, conflict free)
+        const int32_t nb = hist[((uint32_t)(i - ord) & 31u) * kK2Threads];
         const bool main = !delta && i > ord;                        // warm-up covers i = 1..ord (:284-293)
         const int32_t base = H[M];                                  // o[i-1-ord]
         const int32_t nsg = e < 0 ? 1 : -1;                         // -sign(err)
@@ -112,6 +119,7 @@ __device__ __noinline__ void lpc_warp(int32_t *p, const int n, const int nmax, c
         const int32_t x = main ? v : w;
         const int32_t o = (int32_t)((uint32_t)x << sh) >> sh;       // :309-310
         if (live) p[(uint32_t)i * kTile] = o;
+        hist[((uint32_t)i & 31u) * kK2Threads] = o;
         // masked shift: true history up to the lane's order, the new base beyond it
 #pragma unroll
         for (int j = M; j > 0; --j) H[j] = (int32_t)(((uint32_t)nb & msk[j]) | ((uint32_t)H[j - 1] & ~msk[j]));
@@ -119,9 +127,10 @@ __device__ __noinline__ void lpc_warp(int32_t *p, const int n, const int nmax, c
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kK2Threads)
 k2_lpc(const ChunkArgs a)
 {
+    __shared__ int32_t hist_smem[32 * kK2Threads];
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp = (tile, channel)
     const uint32_t tile = gw >> 1;
@@ -147,13 +156,13 @@ k2_lpc(const ChunkArgs a)
     if (maxo == 0) return;
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     int32_t *p = a.planes + ((uint64_t)tile * 2u + (uint32_t)ch) * a.ns * kTile + lane;
-    if (maxo <= 4) lpc_warp<4>(p, n, nmax, rss, ord, q, coef16, active);
-    else if (maxo <= 8) lpc_warp<8>(p, n, nmax, rss, ord, q, coef16, active);
-    else if (maxo <= 12) lpc_warp<12>(p, n, nmax, rss, ord, q, coef16, active);
-    else if (maxo <= 16) lpc_warp<16>(p, n, nmax, rss, ord, q, coef16, active);
-    else if (maxo <= 20) lpc_warp<20>(p, n, nmax, rss, ord, q, coef16, active);
-    else if (maxo <= 24) lpc_warp<24>(p, n, nmax, rss, ord, q, coef16, active);
-    else lpc_warp<30>(p, n, nmax, rss, ord, q, coef16, active);
+    if (maxo <= 4) lpc_warp<4>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    else if (maxo <= 8) lpc_warp<8>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    else if (maxo <= 12) lpc_warp<12>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    else if (maxo <= 16) lpc_warp<16>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    else if (maxo <= 20) lpc_warp<20>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    else if (maxo <= 24) lpc_warp<24>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    else lpc_warp<30>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
 }
 
 cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
@@ -161,7 +170,7 @@ cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
     if (a.n == 0) return cudaSuccess;
     const uint32_t tiles = (a.n + kTile - 1) / kTile;
     const uint32_t warps = tiles * 2;
-    k2_lpc<<<(warps + 3) / 4, 128, 0, st>>>(a);
+    k2_lpc<<<(warps + 3) / 4, kK2Threads, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
