@@ -17,20 +17,14 @@ struct K0Args {
     const uint8_t *arena;
     const FrameRef *refs;
     const TrackCfg *cfgs;
-    uint64_t n_frames;
-    uint32_t n_tracks;
-    const uint64_t *track_first_frame;  // device, n_tracks entries
     FrameDesc *desc;
     FrameCoefs *coefs;
-    uint32_t *out_len;
-    uint64_t *block_sums;     // k0_scan_blocks(n_frames) entries
-    uint64_t *grand_total;    // 1 entry
-    uint64_t *frame_off;      // n_frames entries: unpadded exclusive scan of out_len
-    uint64_t *track_start;    // n_tracks + 1 entries
-    uint32_t *max_samples;    // 1 entry, pre-zeroed: max sample-frames emitted by any frame
+    const uint32_t *expect_len;   // PCM bytes per frame as laid out by the host
+    uint32_t *mismatch;           // incremented when K0's size differs from expect_len
+    uint64_t f0;                  // first frame of this launch (device-local index)
+    uint32_t n;
 };
 cudaError_t launch_k0(const K0Args &a, cudaStream_t st, uint32_t *launches);
-uint32_t k0_scan_blocks(uint64_t n_frames);
 
 // One pipeline chunk = frames [f0, f0 + n) of the device's frame list; planes
 // hold ceil(n / 32) tiles of 2 channels x ns samples x 32 lanes int32.
@@ -40,8 +34,7 @@ struct ChunkArgs {
     const TrackCfg *cfgs;
     FrameDesc *desc;
     const FrameCoefs *coefs;
-    const uint64_t *frame_off;     // unpadded PCM offsets
-    const uint64_t *track_shift;   // per track: padded start - unpadded start
+    const uint64_t *frame_off;     // PCM byte offset of every frame in the global layout
     int32_t *planes;
     uint8_t *pcm;                  // device PCM base (global layout offset `pcm_base` maps to pcm[0])
     uint64_t pcm_base;

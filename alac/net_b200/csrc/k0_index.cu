@@ -1,10 +1,13 @@
-// K0 -- frame-header pre-pass + PCM offset scan.
+// K0 -- frame-header pre-pass.
 //
 // Replaces the header section of AlacFile.DecodeFrame (ALACDecoder/AlacFile.cs
-// :435-475 mono, :584-641 stereo) for every frame at once and turns the
-// demuxer's per-frame sizes into a device-resident index with PCM output
-// offsets (the reference learns each frame's sample count only while decoding
-// it, AlacFile.cs:447-453; AlacContext.cs:199 adds stts durations afterwards).
+// :435-475 mono, :584-641 stereo) for every frame at once: element type,
+// sample count, wasted bytes, escape flag, mix parameters, per-channel
+// predictor / Rice parameters and coefficients, and the bit offsets where the
+// wasted-byte block and the Rice (or raw) data start.  The PCM byte count of
+// each frame follows from tag + hassize + N alone; the host runtime derives
+// the same number from the same seven header bytes when it lays out the output
+// (runtime.cu frame_pcm_bytes), and K0 counts any disagreement.
 //
 // One thread per frame.  Header bits are read through a byte-safe reader that
 // returns 0 for bytes at or past the frame's stsz length, which is how the
@@ -33,11 +36,10 @@ struct SafeReader {
     }
 };
 
-// Parses frame f and returns the number of sample-frames of PCM it emits.
+// Parses frame f and returns the number of PCM bytes it emits.
 __device__ __forceinline__ uint32_t
 parse_one(const uint32_t f, const uint8_t *__restrict__ arena, const FrameRef *__restrict__ refs,
-          const TrackCfg *__restrict__ cfgs, FrameDesc *__restrict__ desc, FrameCoefs *__restrict__ coefs,
-          uint32_t *__restrict__ out_len)
+          const TrackCfg *__restrict__ cfgs, FrameDesc *__restrict__ desc, FrameCoefs *__restrict__ coefs)
 {
     const FrameRef ref = refs[f];
     const TrackCfg cfg = cfgs[ref.track];
@@ -114,126 +116,30 @@ parse_one(const uint32_t f, const uint8_t *__restrict__ arena, const FrameRef *_
     d.status = status;
     desc[f] = d;
     coefs[f] = fc;
-    out_len[f] = d.out_len;
-    return bytes_per_sf ? d.out_len / bytes_per_sf : 0;
+    return d.out_len;
 }
 
 __global__ void __launch_bounds__(128)
 k0_parse_headers(const uint8_t *__restrict__ arena, const FrameRef *__restrict__ refs,
                  const TrackCfg *__restrict__ cfgs, uint32_t n_frames,
                  FrameDesc *__restrict__ desc, FrameCoefs *__restrict__ coefs,
-                 uint32_t *__restrict__ out_len, uint32_t *__restrict__ max_samples)
+                 const uint32_t *__restrict__ expect_len, uint32_t *__restrict__ mismatch)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n_eff = 0;
-    if (f < n_frames) n_eff = parse_one(f, arena, refs, cfgs, desc, coefs, out_len);
-    // plane stride / K3 grid: the longest run of sample-frames any frame emits
-    const uint32_t m = __reduce_max_sync(0xffffffffu, n_eff);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_samples, m);
+    if (f >= n_frames) return;
+    const uint32_t len = parse_one(f, arena, refs, cfgs, desc, coefs);
+    if (len != expect_len[f]) atomicAdd(mismatch, 1u);   // host layout rule out of sync (never expected)
 }
 
-// ---- exclusive scan of out_len (uint32) into uint64 offsets ----------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanBlock = kScanThreads * kScanItems;
-
-__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total)
-{
-    __shared__ uint64_t warp_sums[kScanThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    uint64_t base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kScanThreads / 32; w++) {
-        const uint64_t s = warp_sums[w];
-        if (w < warp) base += s;
-        tot += s;
-    }
-    __syncthreads();
-    *total = tot;
-    return base + incl - v;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k0_scan_block_sums(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ block_sums)
-{
-    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) if (base + k < n) s += in[base + k];
-    uint64_t tot;
-    block_exclusive_scan(s, &tot);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k0_scan_sums(uint64_t *__restrict__ block_sums, uint32_t n_blocks, uint64_t *__restrict__ grand_total)
-{
-    uint64_t carry = 0;
-    for (uint32_t b0 = 0; b0 < n_blocks; b0 += kScanThreads) {
-        const uint32_t i = b0 + threadIdx.x;
-        const uint64_t v = i < n_blocks ? block_sums[i] : 0;
-        uint64_t tot;
-        const uint64_t ex = block_exclusive_scan(v, &tot);
-        if (i < n_blocks) block_sums[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) *grand_total = carry;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k0_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ block_sums,
-              uint64_t *__restrict__ out)
-{
-    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
-    uint64_t tot;
-    uint64_t ex = block_exclusive_scan(s, &tot) + block_sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        if (base + k < n) out[base + k] = ex;
-        ex += v[k];
-    }
-}
-
-// unpadded PCM offset of each track's first frame (tracks with no frames get
-// the offset of the next frame, or the grand total)
-__global__ void k0_gather_track_starts(const uint64_t *__restrict__ frame_off, const uint64_t *__restrict__ grand_total,
-                                       const uint64_t *__restrict__ track_first_frame, uint32_t n_tracks,
-                                       uint64_t n_frames, uint64_t *__restrict__ track_start)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tracks) return;
-    const uint64_t f = t < n_tracks ? track_first_frame[t] : n_frames;
-    track_start[t] = f < n_frames ? frame_off[f] : *grand_total;
-}
-
-// ---- host launchers ---------------------------------------------------------
+// ---- host launcher -----------------------------------------------------------
 cudaError_t launch_k0(const K0Args &a, cudaStream_t st, uint32_t *launches)
 {
-    if (a.n_frames == 0) return cudaSuccess;
-    const uint32_t nb = (uint32_t)((a.n_frames + 127) / 128);
-    k0_parse_headers<<<nb, 128, 0, st>>>(a.arena, a.refs, a.cfgs, (uint32_t)a.n_frames, a.desc, a.coefs, a.out_len, a.max_samples);
-    const uint32_t sb = (uint32_t)((a.n_frames + kScanBlock - 1) / kScanBlock);
-    k0_scan_block_sums<<<sb, kScanThreads, 0, st>>>(a.out_len, a.n_frames, a.block_sums);
-    k0_scan_sums<<<1, kScanThreads, 0, st>>>(a.block_sums, sb, a.grand_total);
-    k0_scan_apply<<<sb, kScanThreads, 0, st>>>(a.out_len, a.n_frames, a.block_sums, a.frame_off);
-    k0_gather_track_starts<<<(a.n_tracks + 1 + 127) / 128, 128, 0, st>>>(a.frame_off, a.grand_total, a.track_first_frame,
-                                                                        a.n_tracks, a.n_frames, a.track_start);
-    if (launches) *launches += 5;
+    if (a.n == 0) return cudaSuccess;
+    const uint32_t nb = (a.n + 127) / 128;
+    k0_parse_headers<<<nb, 128, 0, st>>>(a.arena, a.refs + a.f0, a.cfgs, a.n, a.desc + a.f0, a.coefs + a.f0,
+                                         a.expect_len + a.f0, a.mismatch);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
-
-uint32_t k0_scan_blocks(uint64_t n_frames) { return (uint32_t)((n_frames + kScanBlock - 1) / kScanBlock); }
 
 }  // namespace alacgpu

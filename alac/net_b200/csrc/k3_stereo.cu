@@ -55,7 +55,7 @@ k3_stereo_pack(const ChunkArgs a, const uint32_t blocks_per_tile)
         ss = cfg.sample_size;
         nch = cfg.num_channels;
         n_eff = d.out_len / (uint32_t)((ss >> 3) * nch);
-        out = a.frame_off[f] + a.track_shift[ref.track] - a.pcm_base;
+        out = a.frame_off[f] - a.pcm_base;
         frame_bit = ref.off * 8ull;
     }
     // anything to do for this 32-sample block?

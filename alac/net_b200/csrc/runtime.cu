@@ -1,11 +1,25 @@
 // runtime.cu -- host runtime and C ABI of libalacgpu.so.
 //
-// Owns: the per-device mdat arena and frame index (the device-resident form of
-// the demuxer's stsz table, ALACDecoder/DemuxResT.cs:28), the multi-GPU frame
-// partition, the chunked K1->K2->K3 pipeline, PCM staging back to the caller
-// and the per-frame pull that stands behind AlacContext.Read
+// Owns: the host-side frame index (the demuxer's stsz table turned into
+// {arena offset, length, PCM offset, PCM length} per frame; ALACDecoder/
+// DemuxResT.cs:28, AlacContext.cs:194-195), the per-device mdat arena, the
+// multi-GPU frame partition, the chunked H2D -> K0 -> K1 -> K2 -> K3 -> D2H
+// pipeline, and the per-frame pull that stands behind AlacContext.Read
 // (ALACDecoder/AlacContext.cs:163-204).  No CPU decode path exists here: every
-// sample is produced by the kernels.
+// sample is produced by the kernels.  The only bitstream bytes the host looks
+// at are the first seven of each frame (tag / hassize / sample count), to know
+// how many PCM bytes the frame will produce (AlacFile.cs:435-453 / :584-595) so
+// that the output layout and every copy size are known before any kernel runs.
+//
+// Pipeline.  A frame is a serial chain of ~8k symbols and ~8k predictor steps,
+// so a chunk of frames takes about the same time whether it holds 500 or
+// 15,000 frames; throughput comes from having many frames in flight.  Chunks
+// therefore run CONCURRENTLY on kSlots compute streams (each with its own
+// plane buffer), fed by one H2D stream and drained by one D2H stream:
+//   h2d:   copy(c0) copy(c1) copy(c2) ...
+//   slot0:          K0..K3(c0)            K0..K3(c8) ...
+//   slot1:                   K0..K3(c1)   ...
+//   d2h:                        pcm(c0) pcm(c1) ...
 #include "../../../include/alacgpu.h"
 
 #include <algorithm>
@@ -26,7 +40,8 @@ constexpr uint64_t kTrackAlign = 256;     // PCM start alignment of each track i
 // zero padding after the last staged byte: a lane whose frame is truncated keeps reading
 // (at most 2 channels x 16384 symbols x 59 bits) until K1 flags the overrun at the end
 constexpr uint64_t kArenaTail = 256 * 1024 + 256;
-constexpr uint32_t kDefaultChunkFrames = 32768;
+constexpr uint32_t kMaxChunkFrames = 32768;
+constexpr int kSlots = 8;
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -52,18 +67,32 @@ struct DevBuf {
 
 struct HostTrack {
     alacgpu_track_cfg cfg;
-    const uint8_t *mdat;          // borrowed until prepare()
+    const uint8_t *mdat;          // borrowed until the first prepare()/decode_all() returns
     uint64_t mdat_len;
     uint64_t first_frame_offset;
     uint64_t first_frame;         // index into the global frame list
     uint32_t n_frames;
-    uint64_t pcm_off, pcm_len;    // global (padded) layout, valid after prepare
+    uint64_t pcm_off, pcm_len;    // global (padded) layout
+};
+
+struct HostCopy { const uint8_t *src; uint64_t dst, len; };
+
+struct Chunk {
+    uint64_t f0;                  // device-local first frame
+    uint32_t n;
+    uint32_t copy_lo, copy_hi;    // range in Device::copies
+    uint64_t pcm_lo, pcm_hi;      // global PCM byte range produced by this chunk
+};
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    DevBuf<int32_t> planes;
 };
 
 struct Device {
     int id = 0;
-    cudaStream_t st = nullptr;        // compute
-    cudaStream_t st_copy = nullptr;   // H2D / D2H
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    Slot slots[kSlots];
     // shard = global frames [f_lo, f_hi)
     uint64_t f_lo = 0, f_hi = 0;
     DevBuf<uint8_t> arena;
@@ -72,22 +101,20 @@ struct Device {
     DevBuf<TrackCfg> cfgs;
     DevBuf<FrameDesc> desc;
     DevBuf<FrameCoefs> coefs;
-    DevBuf<uint32_t> out_len;
+    DevBuf<uint32_t> expect_len;
     DevBuf<uint64_t> frame_off;
-    DevBuf<uint64_t> block_sums;
-    DevBuf<uint64_t> track_first;     // per track: first local frame index (or n_local)
-    DevBuf<uint64_t> track_start;     // n_tracks + 1
-    DevBuf<uint64_t> track_shift;     // per track
-    DevBuf<uint64_t> scalars;         // [0] grand total, [1] (u32) max samples, [2] checksum
-    DevBuf<int32_t> planes;
+    DevBuf<uint64_t> scalars;         // [0] K0 size mismatches (u32), [2] checksum
     DevBuf<uint8_t> pcm;
-    DevBuf<int32_t> status32;
-    uint64_t pcm_lo = 0, pcm_hi = 0;  // global byte range of this shard's PCM buffer (pcm_lo 256-aligned)
+    uint64_t pcm_lo = 0, pcm_hi = 0;  // global byte range held by `pcm` (pcm_lo 256-aligned)
     uint64_t pcm_first = 0;           // global offset of the first byte this shard produces
-    uint64_t total_unpadded = 0;
-    uint32_t max_samples = 0;
-    std::vector<uint64_t> h_track_start;
+    uint32_t ns = 32;                 // plane stride (samples), multiple of 32
+    std::vector<FrameRef> h_refs;
+    std::vector<HostCopy> track_copies;   // one per (track, device): host bytes -> arena
+    std::vector<HostCopy> copies;         // the same bytes split at chunk boundaries
+    std::vector<Chunk> chunks;
+    uint32_t chunk_frames = 0;
     std::vector<cudaEvent_t> events;
+    bool resident = false;            // arena bytes + K0 results are on the device
     bool decoded = false;
 };
 
@@ -97,17 +124,18 @@ struct alacgpu_ctx {
     std::vector<Device> devs;
     std::vector<HostTrack> tracks;
     std::vector<uint32_t> sizes;          // stsz of every frame, track-major
+    std::vector<uint32_t> out_len;        // PCM bytes of every frame (host rule == K0 rule)
+    std::vector<uint64_t> frame_off;      // global padded PCM offset of every frame
     alacgpu_opts opts{};
-    bool prepared = false;
+    bool planned = false;
     uint64_t total_pcm = 0;
     uint64_t compressed_bytes = 0;
+    uint32_t max_sf = 0;                  // most sample-frames any frame emits
+    uint32_t index_launches = 0;
     alacgpu_timing timing{};
     std::string err;
-    // read_frame support (host mirrors, filled lazily)
-    std::vector<uint64_t> h_frame_off;    // global padded offset of every frame
-    std::vector<uint32_t> h_frame_len;
     std::vector<int32_t> h_status;
-    bool have_frame_tables = false;
+    bool have_status = false;
     uint8_t *window = nullptr;            // pinned
     uint64_t win_lo = 0, win_hi = 0;
 };
@@ -150,6 +178,25 @@ cudaEvent_t get_event(Device &d, size_t i)
     return d.events[i];
 }
 
+// PCM bytes frame `p[0..len)` decodes to -- the same rule K0 applies on the device
+// (k0_index.cu parse_one): element tag, hassize and the 32-bit sample count are the first
+// 23 (+32) bits of the frame (AlacFile.cs:435-453 / :584-595); bytes past `len` read as 0.
+uint32_t frame_pcm_bytes(const alacgpu_track_cfg &cfg, const uint8_t *p, uint64_t len)
+{
+    uint8_t b[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 7 && (uint64_t)i < len; i++) b[i] = p[i];
+    const uint32_t bpsf = (uint32_t)(cfg.sample_size / 8) * (uint32_t)cfg.num_channels;
+    const uint32_t tag = b[0] >> 5;
+    uint32_t n = (uint32_t)cfg.max_samples_per_frame;
+    if (tag > 1) return n * bpsf;                                   // AlacFile.cs:436-437,:577,:718
+    const uint32_t hassize = (b[2] >> 4) & 1u;                      // bit 19
+    if (hassize)                                                    // bits 23..54
+        n = ((uint32_t)(b[2] & 1u) << 31) | ((uint32_t)b[3] << 23) | ((uint32_t)b[4] << 15) |
+            ((uint32_t)b[5] << 7) | ((uint32_t)b[6] >> 1);
+    if (n > (uint32_t)kMaxFrameSamples || (uint64_t)n * bpsf > (uint64_t)kMaxFramePcmBytes) return 0;
+    return n * bpsf;
+}
+
 // which track holds global frame g (tracks sorted by first_frame)
 size_t track_of(const alacgpu_ctx *ctx, uint64_t g)
 {
@@ -158,20 +205,325 @@ size_t track_of(const alacgpu_ctx *ctx, uint64_t g)
         size_t mid = (lo + hi) / 2;
         if (ctx->tracks[mid].first_frame <= g) lo = mid; else hi = mid;
     }
-    // skip empty tracks that share the same first_frame
     while (lo + 1 < ctx->tracks.size() && ctx->tracks[lo].n_frames == 0) lo++;
     return lo;
 }
 
-int lanes_for(const alacgpu_ctx *ctx, uint32_t n_frames)
+int lanes_for(const alacgpu_ctx *ctx)
 {
     const uint32_t o = ctx->opts.entropy_lanes;
     if (o == 4 || o == 8 || o == 16 || o == 32) return (int)o;
-    // enough warps to cover 148 SMs x 4 schedulers a few times over, else
-    // trade idle lanes for more resident warps (the stage is latency bound)
-    if (n_frames / 32 >= 148u * 12u) return 32;
-    if (n_frames / 16 >= 148u * 12u) return 16;
-    return 8;
+    return 32;
+}
+
+void invalidate(alacgpu_ctx *ctx)
+{
+    ctx->planned = false;
+    ctx->have_status = false;
+    ctx->win_lo = ctx->win_hi = 0;
+    for (Device &d : ctx->devs) { d.resident = false; d.decoded = false; d.chunk_frames = 0; d.chunks.clear(); }
+}
+
+// Partition + per-device frame index.  Pure host work plus allocations and the small table
+// uploads (on the H2D stream, ahead of any mdat copy).
+int32_t build_plan(alacgpu_ctx *ctx)
+{
+    if (ctx->planned) return ALACGPU_OK;
+    const uint64_t n_frames = ctx->sizes.size();
+    const uint32_t n_tracks = (uint32_t)ctx->tracks.size();
+    const int n_dev = (int)ctx->devs.size();
+    std::vector<uint64_t> cut(n_dev + 1);
+    alacgpu_plan_partition(ctx->sizes.data(), n_frames, n_dev, cut.data());
+    uint64_t compressed = 0;
+    std::vector<TrackCfg> cfgs(std::max<uint32_t>(n_tracks, 1));
+    for (uint32_t t = 0; t < n_tracks; t++) {
+        const alacgpu_track_cfg &h = ctx->tracks[t].cfg;
+        TrackCfg c{};
+        c.sample_size = h.sample_size; c.num_channels = h.num_channels;
+        c.max_samples_per_frame = h.max_samples_per_frame;
+        c.rice_history_mult = h.rice_history_mult; c.rice_initial_history = h.rice_initial_history;
+        c.rice_kmodifier = h.rice_kmodifier;
+        cfgs[t] = c;
+    }
+    for (int g = 0; g < n_dev; g++) {
+        Device &d = ctx->devs[g];
+        d.f_lo = cut[g];
+        d.f_hi = cut[g + 1];
+        d.resident = d.decoded = false;
+        d.chunks.clear();
+        d.chunk_frames = 0;
+        const uint64_t n_local = d.f_hi - d.f_lo;
+        CU(cudaSetDevice(d.id));
+        d.h_refs.assign(n_local, FrameRef{});
+        d.track_copies.clear();
+        uint64_t used = 0;
+        for (uint32_t t = 0; t < n_tracks; t++) {
+            const HostTrack &ht = ctx->tracks[t];
+            const uint64_t a = std::max<uint64_t>(ht.first_frame, d.f_lo);
+            const uint64_t b = std::min<uint64_t>(ht.first_frame + ht.n_frames, d.f_hi);
+            if (a >= b) continue;
+            uint64_t off = ht.first_frame_offset;       // byte offset of frame a within the track's mdat
+            for (uint64_t f = ht.first_frame; f < a; f++) off += ctx->sizes[f];
+            const uint64_t base = align_up(used, 16);
+            const uint64_t src_lo = std::min(off, ht.mdat_len);
+            uint64_t cur = off;
+            for (uint64_t f = a; f < b; f++) {
+                FrameRef r;
+                const uint64_t avail = cur < ht.mdat_len ? ht.mdat_len - cur : 0;
+                r.len = (uint32_t)std::min<uint64_t>(ctx->sizes[f], avail);   // short read (MyStream.cs:47-52)
+                r.off = r.len ? base + (cur - src_lo) : base;
+                r.track = t;
+                d.h_refs[f - d.f_lo] = r;
+                compressed += r.len;
+                cur += ctx->sizes[f];
+            }
+            const uint64_t src_hi = std::min(cur, ht.mdat_len);
+            if (src_hi > src_lo) d.track_copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo});
+            used = base + (src_hi - src_lo);
+        }
+        d.arena_used = used;
+        d.ns = std::max<uint32_t>((ctx->max_sf + 31u) & ~31u, 32u);
+        // PCM byte range of the shard (contiguous in the global layout)
+        if (n_local) {
+            d.pcm_first = ctx->frame_off[d.f_lo];
+            d.pcm_lo = d.pcm_first / kTrackAlign * kTrackAlign;
+            d.pcm_hi = ctx->frame_off[d.f_hi - 1] + ctx->out_len[d.f_hi - 1];
+        } else {
+            d.pcm_first = d.pcm_lo = d.pcm_hi = 0;
+        }
+        CU(d.arena.reserve(used + kArenaTail));
+        CU(d.refs.reserve(std::max<uint64_t>(n_local, 1)));
+        CU(d.cfgs.reserve(cfgs.size()));
+        CU(d.desc.reserve(std::max<uint64_t>(n_local, 1)));
+        CU(d.coefs.reserve(std::max<uint64_t>(n_local, 1)));
+        CU(d.expect_len.reserve(std::max<uint64_t>(n_local, 1)));
+        CU(d.frame_off.reserve(std::max<uint64_t>(n_local, 1)));
+        CU(d.scalars.reserve(4));
+        CU(d.pcm.reserve(d.pcm_hi - d.pcm_lo + 64));
+        // small tables first, on the same stream the mdat copies will use
+        CU(cudaMemsetAsync(d.arena.p + used, 0, kArenaTail, d.st_h2d));
+        if (n_local) {
+            CU(cudaMemcpyAsync(d.refs.p, d.h_refs.data(), n_local * sizeof(FrameRef), cudaMemcpyHostToDevice, d.st_h2d));
+            CU(cudaMemcpyAsync(d.expect_len.p, ctx->out_len.data() + d.f_lo, n_local * sizeof(uint32_t), cudaMemcpyHostToDevice, d.st_h2d));
+            CU(cudaMemcpyAsync(d.frame_off.p, ctx->frame_off.data() + d.f_lo, n_local * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st_h2d));
+        }
+        CU(cudaMemcpyAsync(d.cfgs.p, cfgs.data(), cfgs.size() * sizeof(TrackCfg), cudaMemcpyHostToDevice, d.st_h2d));
+        CU(cudaMemsetAsync(d.scalars.p, 0, 4 * sizeof(uint64_t), d.st_h2d));
+        // alignment gaps between tracks (and below the shard's first byte) are zero bytes
+        if (n_local) {
+            const size_t t0 = track_of(ctx, d.f_lo), t1 = track_of(ctx, d.f_hi - 1);
+            if (d.pcm_first > d.pcm_lo) CU(cudaMemsetAsync(d.pcm.p, 0, d.pcm_first - d.pcm_lo, d.st_h2d));
+            for (size_t t = t0; t < t1; t++) {
+                const uint64_t end = ctx->tracks[t].pcm_off + ctx->tracks[t].pcm_len, nxt = ctx->tracks[t + 1].pcm_off;
+                if (nxt > end && end >= d.pcm_lo && nxt <= d.pcm_hi)
+                    CU(cudaMemsetAsync(d.pcm.p + (end - d.pcm_lo), 0, nxt - end, d.st_h2d));
+            }
+        }
+    }
+    // `cfgs` is a local and the tables must precede every kernel: finish the uploads now
+    for (Device &d : ctx->devs) {
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.st_h2d));
+    }
+    ctx->compressed_bytes = compressed;
+    ctx->planned = true;
+    return ALACGPU_OK;
+}
+
+// Split the device's frames into chunks of `cf` frames and split the host->arena copies at
+// the chunk boundaries, so chunk c never waits for bytes of chunk c+1.
+void build_chunks(alacgpu_ctx *ctx, Device &d, uint32_t cf)
+{
+    if (d.chunk_frames == cf && !d.chunks.empty()) return;
+    d.chunks.clear();
+    d.copies.clear();
+    const uint64_t n_local = d.f_hi - d.f_lo;
+    for (uint64_t f0 = 0; f0 < n_local; f0 += cf) {
+        Chunk c{};
+        c.f0 = f0;
+        c.n = (uint32_t)std::min<uint64_t>(cf, n_local - f0);
+        c.copy_lo = (uint32_t)d.copies.size();
+        uint64_t f = f0;
+        while (f < f0 + c.n) {                      // runs of frames of one track inside the chunk
+            const uint32_t t = d.h_refs[f].track;
+            uint64_t e = f;
+            uint64_t lo = ~0ull, hi = 0;            // arena bytes of the run (empty frames carry none)
+            while (e < f0 + c.n && d.h_refs[e].track == t) {
+                const FrameRef &r = d.h_refs[e];
+                if (r.len) { lo = std::min<uint64_t>(lo, r.off); hi = std::max<uint64_t>(hi, r.off + r.len); }
+                e++;
+            }
+            if (hi > lo)
+                for (const HostCopy &hc : d.track_copies)       // one staged range per (track, device)
+                    if (lo >= hc.dst && lo < hc.dst + hc.len) {
+                        d.copies.push_back({hc.src + (lo - hc.dst), lo, std::min(hi, hc.dst + hc.len) - lo});
+                        break;
+                    }
+            f = e;
+        }
+        c.copy_hi = (uint32_t)d.copies.size();
+        c.pcm_lo = ctx->frame_off[d.f_lo + f0];
+        c.pcm_hi = ctx->frame_off[d.f_lo + f0 + c.n - 1] + ctx->out_len[d.f_lo + f0 + c.n - 1];
+        d.chunks.push_back(c);
+    }
+    d.chunk_frames = cf;
+}
+
+constexpr size_t kEvPerChunk = 6;   // start, after K0, K1, K2, K3, h2d-done
+constexpr size_t kEvBase = 4;       // [0] pipeline start, [1] pipeline end, [2] d2h start, [3] d2h end
+
+// Issue one chunk's kernels on its slot stream.
+int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool with_k0, bool with_decode,
+                    size_t ev, uint32_t *launches)
+{
+    ChunkArgs ca{};
+    ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
+    ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
+    ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n;
+    CU(cudaEventRecord(get_event(d, ev), s.st));
+    if (with_k0) {
+        K0Args ka{};
+        ka.arena = d.arena.p; ka.refs = d.refs.p; ka.cfgs = d.cfgs.p; ka.desc = d.desc.p; ka.coefs = d.coefs.p;
+        ka.expect_len = d.expect_len.p; ka.mismatch = reinterpret_cast<uint32_t *>(d.scalars.p);
+        ka.f0 = c.f0; ka.n = c.n;
+        CU(launch_k0(ka, s.st, launches));
+    }
+    CU(cudaEventRecord(get_event(d, ev + 1), s.st));
+    if (with_decode) CU(launch_k1(ca, lanes_for(ctx), s.st, launches));
+    CU(cudaEventRecord(get_event(d, ev + 2), s.st));
+    if (with_decode) CU(launch_k2(ca, s.st, launches));
+    CU(cudaEventRecord(get_event(d, ev + 3), s.st));
+    if (with_decode) CU(launch_k3(ca, s.st, launches));
+    CU(cudaEventRecord(get_event(d, ev + 4), s.st));
+    return ALACGPU_OK;
+}
+
+// The whole pipeline on every device.  stage: copy mdat to the arena (chunk by chunk);
+// index: run K0; decode: run K1-K3; pcm_dst: copy PCM back chunk by chunk.
+int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint8_t *pcm_dst, uint32_t *launches_out)
+{
+    const int n_dev = (int)ctx->devs.size();
+    uint32_t launches = 0, chunks_total = 0;
+    for (int g = 0; g < n_dev; g++) {
+        Device &d = ctx->devs[g];
+        const uint64_t n_local = d.f_hi - d.f_lo;
+        if (!n_local) continue;
+        CU(cudaSetDevice(d.id));
+        // chunk size: as much as possible in flight at once when the bytes are already
+        // resident; ~kSlots chunks when streaming from the host so copies and kernels overlap
+        uint32_t cf = ctx->opts.chunk_frames;
+        if (!cf) {
+            if (stage) cf = (uint32_t)std::max<uint64_t>(256, (n_local + kSlots - 1) / kSlots);
+            else cf = (uint32_t)std::min<uint64_t>(n_local, kMaxChunkFrames);
+        }
+        cf = std::min<uint32_t>((cf + 31u) & ~31u, kMaxChunkFrames);
+        build_chunks(ctx, d, cf);
+        const size_t n_chunks = d.chunks.size();
+        const int slots_used = (int)std::min<size_t>(kSlots, n_chunks);
+        if (decode)
+            for (int s = 0; s < slots_used; s++) CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
+        get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
+        CU(cudaEventRecord(d.events[0], d.slots[0].st));
+        for (int s = 1; s < slots_used; s++) CU(cudaStreamWaitEvent(d.slots[s].st, d.events[0], 0));
+        if (pcm_dst) {
+            CU(cudaStreamWaitEvent(d.st_d2h, d.events[0], 0));
+            CU(cudaEventRecord(d.events[2], d.st_d2h));
+        }
+        for (size_t ci = 0; ci < n_chunks; ci++) {
+            const Chunk &c = d.chunks[ci];
+            Slot &s = d.slots[ci % kSlots];
+            const size_t ev = kEvBase + ci * kEvPerChunk;
+            if (stage) {
+                for (uint32_t k = c.copy_lo; k < c.copy_hi; k++)
+                    CU(cudaMemcpyAsync(d.arena.p + d.copies[k].dst, d.copies[k].src, d.copies[k].len,
+                                       cudaMemcpyHostToDevice, d.st_h2d));
+                CU(cudaEventRecord(d.events[ev + 5], d.st_h2d));
+                CU(cudaStreamWaitEvent(s.st, d.events[ev + 5], 0));
+            }
+            int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &launches);
+            if (r) return r;
+            if (pcm_dst && decode && c.pcm_hi > c.pcm_lo) {
+                CU(cudaStreamWaitEvent(d.st_d2h, d.events[ev + 4], 0));
+                CU(cudaMemcpyAsync(pcm_dst + c.pcm_lo, d.pcm.p + (c.pcm_lo - d.pcm_lo), c.pcm_hi - c.pcm_lo,
+                                   cudaMemcpyDeviceToHost, d.st_d2h));
+            }
+            chunks_total++;
+        }
+        // join: slot 0 waits for the last chunk of every other slot, then stamps the end
+        for (size_t ci = n_chunks > (size_t)kSlots ? n_chunks - kSlots : 0; ci < n_chunks; ci++)
+            if (ci % kSlots != 0) CU(cudaStreamWaitEvent(d.slots[0].st, d.events[kEvBase + ci * kEvPerChunk + 4], 0));
+        CU(cudaEventRecord(d.events[1], d.slots[0].st));
+        if (pcm_dst) CU(cudaEventRecord(d.events[3], d.st_d2h));
+    }
+    // ---- wait + timings --------------------------------------------------------
+    float k0 = 0, k1 = 0, k2 = 0, k3 = 0, kall = 0, d2h = 0, h2d = 0;
+    for (int g = 0; g < n_dev; g++) {
+        Device &d = ctx->devs[g];
+        if (d.f_hi == d.f_lo) continue;
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.slots[0].st));
+        if (pcm_dst) CU(cudaStreamSynchronize(d.st_d2h));
+        if (stage) CU(cudaStreamSynchronize(d.st_h2d));
+        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, ms = 0;
+        for (size_t ci = 0; ci < d.chunks.size(); ci++) {
+            const size_t ev = kEvBase + ci * kEvPerChunk;
+            cudaEventElapsedTime(&ms, d.events[ev], d.events[ev + 1]); s0 += ms;
+            cudaEventElapsedTime(&ms, d.events[ev + 1], d.events[ev + 2]); s1 += ms;
+            cudaEventElapsedTime(&ms, d.events[ev + 2], d.events[ev + 3]); s2 += ms;
+            cudaEventElapsedTime(&ms, d.events[ev + 3], d.events[ev + 4]); s3 += ms;
+        }
+        cudaEventElapsedTime(&ms, d.events[0], d.events[1]);
+        k0 = std::max(k0, s0); k1 = std::max(k1, s1); k2 = std::max(k2, s2); k3 = std::max(k3, s3);
+        kall = std::max(kall, ms);
+        if (pcm_dst) { cudaEventElapsedTime(&ms, d.events[2], d.events[3]); d2h = std::max(d2h, ms); }
+        if (stage) {
+            cudaEventElapsedTime(&ms, d.events[0], d.events[kEvBase + (d.chunks.size() - 1) * kEvPerChunk + 5]);
+            h2d = std::max(h2d, ms);
+        }
+        if (stage || index) d.resident = true;
+        if (decode) d.decoded = true;
+        if (index) {
+            uint32_t mism = 0;
+            CU(cudaMemcpy(&mism, d.scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            if (mism) return fail(ctx, ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size");
+        }
+    }
+    alacgpu_timing &tm = ctx->timing;
+    if (index) tm.index_ms = k0;
+    if (decode) { tm.entropy_ms = k1; tm.lpc_ms = k2; tm.stereo_ms = k3; }
+    tm.kernels_ms = kall;
+    if (stage) tm.h2d_ms = h2d;
+    if (pcm_dst) tm.d2h_ms = d2h;
+    tm.chunks = chunks_total;
+    if (launches_out) *launches_out = launches;
+    ctx->have_status = false;
+    return ALACGPU_OK;
+}
+
+void fill_totals(alacgpu_ctx *ctx)
+{
+    uint64_t samples = 0, pcm = 0;
+    for (const HostTrack &ht : ctx->tracks) {
+        samples += ht.pcm_len / (uint64_t)(ht.cfg.sample_size / 8);
+        pcm += ht.pcm_len;
+    }
+    ctx->timing.compressed_bytes = ctx->compressed_bytes;
+    ctx->timing.pcm_bytes = pcm;
+    ctx->timing.samples = samples;
+}
+
+bool all_resident(alacgpu_ctx *ctx)
+{
+    if (!ctx->planned) return false;
+    for (Device &d : ctx->devs) if (d.f_hi > d.f_lo && !d.resident) return false;
+    return true;
+}
+
+bool all_decoded(alacgpu_ctx *ctx)
+{
+    if (!ctx->planned) return false;
+    for (Device &d : ctx->devs) if (d.f_hi > d.f_lo && !d.decoded) return false;
+    return true;
 }
 
 }  // namespace
@@ -218,21 +570,21 @@ int32_t alacgpu_create(const int32_t *device_ids, int32_t n_devices, const alacg
         size_t n = std::min<size_t>(opts->struct_size ? opts->struct_size : sizeof(alacgpu_opts), sizeof(alacgpu_opts));
         memcpy(&ctx->opts, opts, n);
     }
-    if (ctx->opts.chunk_frames == 0) ctx->opts.chunk_frames = kDefaultChunkFrames;
-    ctx->opts.chunk_frames = (ctx->opts.chunk_frames + 31u) & ~31u;
     std::vector<int> ids;
     if (!device_ids || n_devices <= 0) ids.push_back(0);
     else ids.assign(device_ids, device_ids + n_devices);
     for (int id : ids) {
         if (id < 0 || id >= count) { delete ctx; return ALACGPU_ERR_NO_DEVICE; }
-        Device d;
-        d.id = id;
-        ctx->devs.push_back(std::move(d));
+        ctx->devs.emplace_back();
+        ctx->devs.back().id = id;
     }
     for (Device &d : ctx->devs) {
-        if (cudaSetDevice(d.id) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.st_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        bool ok = cudaSetDevice(d.id) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.st_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.st_d2h, cudaStreamNonBlocking) == cudaSuccess;
+        for (int s = 0; ok && s < kSlots; s++)
+            ok = cudaStreamCreateWithFlags(&d.slots[s].st, cudaStreamNonBlocking) == cudaSuccess;
+        if (!ok) {
             cudaGetLastError();
             alacgpu_destroy(ctx);
             return ALACGPU_ERR_NO_DEVICE;
@@ -247,15 +599,13 @@ int32_t alacgpu_destroy(alacgpu_ctx *ctx)
     if (!ctx) return ALACGPU_OK;
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
-        if (d.st) cudaStreamSynchronize(d.st);
-        if (d.st_copy) cudaStreamSynchronize(d.st_copy);
+        cudaDeviceSynchronize();
         d.arena.release(); d.refs.release(); d.cfgs.release(); d.desc.release(); d.coefs.release();
-        d.out_len.release(); d.frame_off.release(); d.block_sums.release(); d.track_first.release();
-        d.track_start.release(); d.track_shift.release(); d.scalars.release(); d.planes.release();
-        d.pcm.release(); d.status32.release();
+        d.expect_len.release(); d.frame_off.release(); d.scalars.release(); d.pcm.release();
+        for (Slot &s : d.slots) { s.planes.release(); if (s.st) cudaStreamDestroy(s.st); }
         for (cudaEvent_t e : d.events) cudaEventDestroy(e);
-        if (d.st) cudaStreamDestroy(d.st);
-        if (d.st_copy) cudaStreamDestroy(d.st_copy);
+        if (d.st_h2d) cudaStreamDestroy(d.st_h2d);
+        if (d.st_d2h) cudaStreamDestroy(d.st_d2h);
     }
     if (ctx->window) cudaFreeHost(ctx->window);
     delete ctx;
@@ -284,11 +634,26 @@ int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const 
     t.first_frame_offset = first_frame_offset;
     t.first_frame = ctx->sizes.size();
     t.n_frames = n_frames;
+    // output layout: every frame's PCM size follows from its first seven bytes
+    t.pcm_off = align_up(ctx->total_pcm, kTrackAlign);
+    uint64_t off = first_frame_offset, pcm = t.pcm_off;
     ctx->sizes.insert(ctx->sizes.end(), frame_sizes, frame_sizes + n_frames);
+    ctx->out_len.reserve(ctx->out_len.size() + n_frames);
+    ctx->frame_off.reserve(ctx->frame_off.size() + n_frames);
+    for (uint32_t f = 0; f < n_frames; f++) {
+        const uint64_t avail = off < mdat_len ? mdat_len - off : 0;
+        const uint64_t len = std::min<uint64_t>(frame_sizes[f], avail);
+        const uint32_t bytes = frame_pcm_bytes(*cfg, mdat + std::min(off, mdat_len), len);
+        ctx->out_len.push_back(bytes);
+        ctx->frame_off.push_back(pcm);
+        ctx->max_sf = std::max<uint32_t>(ctx->max_sf, bytes / (uint32_t)bpsf);
+        pcm += bytes;
+        off += frame_sizes[f];
+    }
+    t.pcm_len = pcm - t.pcm_off;
+    ctx->total_pcm = pcm;
     ctx->tracks.push_back(t);
-    ctx->prepared = false;
-    ctx->have_frame_tables = false;
-    for (Device &d : ctx->devs) d.decoded = false;
+    invalidate(ctx);
     if (track_id) *track_id = (int32_t)ctx->tracks.size() - 1;
     return ALACGPU_OK;
 }
@@ -298,11 +663,12 @@ int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx)
     if (!ctx) return ALACGPU_ERR_INVALID_ARG;
     ctx->tracks.clear();
     ctx->sizes.clear();
-    ctx->prepared = false;
-    ctx->have_frame_tables = false;
+    ctx->out_len.clear();
+    ctx->frame_off.clear();
     ctx->total_pcm = 0;
-    ctx->win_lo = ctx->win_hi = 0;
-    for (Device &d : ctx->devs) { d.decoded = false; d.f_lo = d.f_hi = 0; }
+    ctx->max_sf = 0;
+    invalidate(ctx);
+    for (Device &d : ctx->devs) d.f_lo = d.f_hi = 0;
     return ALACGPU_OK;
 }
 
@@ -314,7 +680,7 @@ int32_t alacgpu_plan_partition(const uint32_t *frame_sizes, uint64_t n_frames, i
     cut[0] = 0;
     uint64_t acc = 0, f = 0;
     for (int32_t p = 1; p < n_parts; p++) {
-        // smallest f with prefix(f) >= total * p / n_parts (ties: fewer frames on the left)
+        // cut after the frame whose midpoint crosses total * p / n_parts
         const long double target = (long double)total * p / n_parts;
         while (f < n_frames && (long double)acc + frame_sizes[f] / 2.0L <= target) acc += frame_sizes[f++];
         cut[p] = f;
@@ -323,316 +689,68 @@ int32_t alacgpu_plan_partition(const uint32_t *frame_sizes, uint64_t n_frames, i
     return ALACGPU_OK;
 }
 
-// ---------------------------------------------------------------------------
-static int32_t prepare_impl(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes, const bool restage)
+int32_t alacgpu_total_pcm_bytes(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
 {
-    const double t_begin = now_ms();
-    const uint64_t n_frames = ctx->sizes.size();
-    const uint32_t n_tracks = (uint32_t)ctx->tracks.size();
-    const int n_dev = (int)ctx->devs.size();
-    ctx->timing = alacgpu_timing{};
-
-    std::vector<uint64_t> cut(n_dev + 1);
-    alacgpu_plan_partition(ctx->sizes.data(), n_frames, n_dev, cut.data());
-
-    uint64_t compressed = 0;
-    // ---- per device: stage its byte ranges, upload the index, run K0 --------
-    struct Stage {
-        std::vector<FrameRef> refs;
-        std::vector<TrackCfg> cfgs;
-        std::vector<uint64_t> tfirst;
-        uint64_t sc[2] = {0, 0};
-    };
-    std::vector<Stage> stage(n_dev);
-    for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        Stage &sg = stage[g];
-        d.f_lo = cut[g];
-        d.f_hi = cut[g + 1];
-        d.decoded = false;
-        const uint64_t n_local = d.f_hi - d.f_lo;
-        CU(cudaSetDevice(d.id));
-        if (!restage) {
-            // index only: the arena, FrameRef[] and TrackCfg[] staged earlier are still resident
-            cudaEvent_t e0 = get_event(d, 0), e1 = get_event(d, 1), e2 = get_event(d, 2);
-            CU(cudaEventRecord(e0, d.st));
-            CU(cudaMemsetAsync(d.scalars.p, 0, 4 * sizeof(uint64_t), d.st));
-            CU(cudaEventRecord(e1, d.st));
-            K0Args ka{};
-            ka.arena = d.arena.p; ka.refs = d.refs.p; ka.cfgs = d.cfgs.p; ka.n_frames = n_local; ka.n_tracks = n_tracks;
-            ka.track_first_frame = d.track_first.p; ka.desc = d.desc.p; ka.coefs = d.coefs.p; ka.out_len = d.out_len.p;
-            ka.block_sums = d.block_sums.p; ka.grand_total = d.scalars.p; ka.frame_off = d.frame_off.p;
-            ka.track_start = d.track_start.p; ka.max_samples = reinterpret_cast<uint32_t *>(d.scalars.p + 1);
-            if (n_local) CU(launch_k0(ka, d.st, &ctx->timing.kernel_launches));
-            CU(cudaEventRecord(e2, d.st));
-            CU(cudaMemcpyAsync(d.h_track_start.data(), d.track_start.p, (n_tracks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
-            CU(cudaMemcpyAsync(sg.sc, d.scalars.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
-            continue;
-        }
-        sg.refs.resize(n_local);
-        sg.cfgs.resize(std::max<uint32_t>(n_tracks, 1));
-        sg.tfirst.resize(std::max<uint32_t>(n_tracks, 1));
-        struct Copy { const uint8_t *src; uint64_t dst, len; };
-        std::vector<Copy> copies;
-        uint64_t used = 0;
-        for (uint32_t t = 0; t < n_tracks; t++) {
-            const HostTrack &ht = ctx->tracks[t];
-            TrackCfg c{};
-            c.sample_size = ht.cfg.sample_size; c.num_channels = ht.cfg.num_channels;
-            c.max_samples_per_frame = ht.cfg.max_samples_per_frame;
-            c.rice_history_mult = ht.cfg.rice_history_mult;
-            c.rice_initial_history = ht.cfg.rice_initial_history;
-            c.rice_kmodifier = ht.cfg.rice_kmodifier;
-            sg.cfgs[t] = c;
-            const uint64_t a = std::max<uint64_t>(ht.first_frame, d.f_lo);
-            const uint64_t b = std::min<uint64_t>(ht.first_frame + ht.n_frames, d.f_hi);
-            // local index of the track's first frame if this device owns it, else n_local
-            sg.tfirst[t] = (ht.first_frame >= d.f_lo && ht.first_frame < d.f_hi) ? ht.first_frame - d.f_lo : n_local;
-            if (a >= b) continue;
-            uint64_t off = ht.first_frame_offset;       // byte offset of frame a within the track's mdat
-            for (uint64_t f = ht.first_frame; f < a; f++) off += ctx->sizes[f];
-            const uint64_t base = align_up(used, 16);
-            const uint64_t src_lo = std::min(off, ht.mdat_len);
-            uint64_t cur = off;
-            for (uint64_t f = a; f < b; f++) {
-                FrameRef r;
-                const uint64_t avail = cur < ht.mdat_len ? ht.mdat_len - cur : 0;
-                r.len = (uint32_t)std::min<uint64_t>(ctx->sizes[f], avail);   // short read (MyStream.cs:47-52)
-                r.off = r.len ? base + (cur - src_lo) : base;
-                r.track = t;
-                sg.refs[f - d.f_lo] = r;
-                compressed += r.len;
-                cur += ctx->sizes[f];
-            }
-            const uint64_t src_hi = std::min(cur, ht.mdat_len);
-            if (src_hi > src_lo) copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo});
-            used = base + (src_hi - src_lo);
-        }
-        d.arena_used = used;
-        CU(d.arena.reserve(used + kArenaTail));
-        CU(d.refs.reserve(std::max<uint64_t>(n_local, 1)));
-        CU(d.cfgs.reserve(sg.cfgs.size()));
-        CU(d.desc.reserve(std::max<uint64_t>(n_local, 1)));
-        CU(d.coefs.reserve(std::max<uint64_t>(n_local, 1)));
-        CU(d.out_len.reserve(std::max<uint64_t>(n_local, 1)));
-        CU(d.frame_off.reserve(std::max<uint64_t>(n_local, 1)));
-        CU(d.block_sums.reserve(std::max<uint32_t>(k0_scan_blocks(n_local), 1)));
-        CU(d.track_first.reserve(sg.cfgs.size()));
-        CU(d.track_start.reserve(n_tracks + 1));
-        CU(d.track_shift.reserve(sg.cfgs.size()));
-        CU(d.scalars.reserve(4));
-        d.h_track_start.assign(n_tracks + 1, 0);
-
-        cudaEvent_t e0 = get_event(d, 0), e1 = get_event(d, 1), e2 = get_event(d, 2);
-        CU(cudaEventRecord(e0, d.st));
-        for (const Copy &c : copies)
-            CU(cudaMemcpyAsync(d.arena.p + c.dst, c.src, c.len, cudaMemcpyHostToDevice, d.st));
-        CU(cudaMemsetAsync(d.arena.p + used, 0, kArenaTail, d.st));
-        if (n_local) CU(cudaMemcpyAsync(d.refs.p, sg.refs.data(), n_local * sizeof(FrameRef), cudaMemcpyHostToDevice, d.st));
-        CU(cudaMemcpyAsync(d.cfgs.p, sg.cfgs.data(), sg.cfgs.size() * sizeof(TrackCfg), cudaMemcpyHostToDevice, d.st));
-        CU(cudaMemcpyAsync(d.track_first.p, sg.tfirst.data(), sg.tfirst.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
-        CU(cudaMemsetAsync(d.scalars.p, 0, 4 * sizeof(uint64_t), d.st));
-        CU(cudaEventRecord(e1, d.st));
-        K0Args ka{};
-        ka.arena = d.arena.p; ka.refs = d.refs.p; ka.cfgs = d.cfgs.p; ka.n_frames = n_local; ka.n_tracks = n_tracks;
-        ka.track_first_frame = d.track_first.p; ka.desc = d.desc.p; ka.coefs = d.coefs.p; ka.out_len = d.out_len.p;
-        ka.block_sums = d.block_sums.p; ka.grand_total = d.scalars.p; ka.frame_off = d.frame_off.p;
-        ka.track_start = d.track_start.p; ka.max_samples = reinterpret_cast<uint32_t *>(d.scalars.p + 1);
-        if (n_local) {
-            CU(launch_k0(ka, d.st, &ctx->timing.kernel_launches));
-        } else {
-            CU(cudaMemsetAsync(d.track_start.p, 0, (n_tracks + 1) * sizeof(uint64_t), d.st));
-        }
-        CU(cudaEventRecord(e2, d.st));
-        CU(cudaMemcpyAsync(d.h_track_start.data(), d.track_start.p, (n_tracks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
-        CU(cudaMemcpyAsync(sg.sc, d.scalars.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
-    }
-    for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.st));
-        d.total_unpadded = stage[g].sc[0];
-        d.max_samples = (uint32_t)(stage[g].sc[1] & 0xffffffffu);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, d.events[0], d.events[1]); ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, ms);
-        cudaEventElapsedTime(&ms, d.events[1], d.events[2]); ctx->timing.index_ms = std::max(ctx->timing.index_ms, ms);
-    }
-
-    // ---- global layout: tracks at 256-byte aligned offsets -------------------
-    std::vector<uint64_t> dev_base(n_dev + 1, 0);
-    for (int g = 0; g < n_dev; g++) dev_base[g + 1] = dev_base[g] + ctx->devs[g].total_unpadded;
-    // unpadded global start of every track (+ grand total at the end)
-    std::vector<uint64_t> ts(n_tracks + 1, dev_base[n_dev]);
-    for (uint32_t t = 0; t < n_tracks; t++) {
-        const HostTrack &ht = ctx->tracks[t];
-        // device that owns the track's first frame
-        int g = 0;
-        while (g + 1 < n_dev && ht.first_frame >= ctx->devs[g].f_hi) g++;
-        if (ht.first_frame >= n_frames) ts[t] = dev_base[n_dev];
-        else ts[t] = dev_base[g] + ctx->devs[g].h_track_start[t];
-    }
-    uint64_t pos = 0;
-    std::vector<uint64_t> shift(std::max<uint32_t>(n_tracks, 1), 0);
-    for (uint32_t t = 0; t < n_tracks; t++) {
-        HostTrack &ht = ctx->tracks[t];
-        pos = align_up(pos, kTrackAlign);
-        ht.pcm_off = pos;
-        ht.pcm_len = ts[t + 1] - ts[t];
-        shift[t] = pos - ts[t];          // mod 2^64
-        pos += ht.pcm_len;
-    }
-    ctx->total_pcm = pos;
-    uint64_t samples = 0;
-    for (const HostTrack &ht : ctx->tracks) samples += ht.pcm_len / (uint64_t)(ht.cfg.sample_size / 8);
-    for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        CU(cudaSetDevice(d.id));
-        // device-local frame_off is relative to the device's first frame: fold dev_base into the shift
-        std::vector<uint64_t> sh(shift);
-        for (uint64_t &v : sh) v += dev_base[g];
-        CU(cudaMemcpyAsync(d.track_shift.p, sh.data(), sh.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d.st));
-        CU(cudaStreamSynchronize(d.st));
-        // PCM byte range of the shard
-        if (d.f_hi > d.f_lo) {
-            const size_t t0 = track_of(ctx, d.f_lo);
-            d.pcm_first = dev_base[g] + shift[t0];                   // offset of frame f_lo
-            d.pcm_lo = d.pcm_first / kTrackAlign * kTrackAlign;
-            const size_t t1 = track_of(ctx, d.f_hi - 1);
-            d.pcm_hi = dev_base[g + 1] + shift[t1];
-        } else {
-            d.pcm_lo = d.pcm_hi = d.pcm_first = 0;
-        }
-    }
-    if (restage) ctx->compressed_bytes = compressed;
-    ctx->timing.compressed_bytes = ctx->compressed_bytes;
-    ctx->timing.pcm_bytes = dev_base[n_dev];
-    ctx->timing.samples = samples;
-    ctx->timing.total_ms = (float)(now_ms() - t_begin);
-    ctx->prepared = true;
-    ctx->have_frame_tables = false;
-    ctx->win_lo = ctx->win_hi = 0;
-    if (total_pcm_bytes) *total_pcm_bytes = ctx->total_pcm;
+    if (!ctx || !total_pcm_bytes) return ALACGPU_ERR_INVALID_ARG;
+    *total_pcm_bytes = ctx->total_pcm;
     return ALACGPU_OK;
 }
 
 int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes)
 {
     if (!ctx) return ALACGPU_ERR_INVALID_ARG;
-    if (ctx->prepared) { if (total_pcm_bytes) *total_pcm_bytes = ctx->total_pcm; return ALACGPU_OK; }
-    return prepare_impl(ctx, total_pcm_bytes, true);
+    if (!all_resident(ctx)) {
+        const double t0 = now_ms();
+        int32_t r = build_plan(ctx);
+        if (r) return r;
+        ctx->timing = alacgpu_timing{};
+        r = run_pipeline(ctx, /*stage=*/true, /*index=*/true, /*decode=*/false, nullptr, &ctx->index_launches);
+        if (r) return r;
+        fill_totals(ctx);
+        ctx->timing.kernel_launches = ctx->index_launches;
+        ctx->timing.total_ms = (float)(now_ms() - t0);
+    }
+    if (total_pcm_bytes) *total_pcm_bytes = ctx->total_pcm;
+    return ALACGPU_OK;
 }
 
 int32_t alacgpu_reindex(alacgpu_ctx *ctx)
 {
     if (!ctx) return ALACGPU_ERR_INVALID_ARG;
-    if (!ctx->prepared) return prepare_impl(ctx, nullptr, true);
-    return prepare_impl(ctx, nullptr, false);
+    int32_t r = alacgpu_prepare(ctx, nullptr);
+    if (r) return r;
+    const double t0 = now_ms();
+    ctx->timing = alacgpu_timing{};
+    r = run_pipeline(ctx, false, true, false, nullptr, &ctx->index_launches);
+    fill_totals(ctx);
+    ctx->timing.kernel_launches = ctx->index_launches;
+    ctx->timing.total_ms = (float)(now_ms() - t0);
+    return r;
 }
 
-// ---------------------------------------------------------------------------
 int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uint64_t *track_pcm_off,
                            uint64_t *track_pcm_len, int32_t *frame_status)
 {
     if (!ctx) return ALACGPU_ERR_INVALID_ARG;
-    if (!ctx->prepared) {
-        int32_t r = alacgpu_prepare(ctx, nullptr);
-        if (r != ALACGPU_OK) return r;
-    }
-    if (pcm_dst && cap < ctx->total_pcm) return fail(ctx, ALACGPU_ERR_CAPACITY, "pcm_dst smaller than alacgpu_prepare's total");
-    const double t_begin = now_ms();
-    const int n_dev = (int)ctx->devs.size();
-    const uint32_t chunk_frames = ctx->opts.chunk_frames;
-    uint32_t launches = 0, chunks_total = 0;
-
-    // ---- issue: all devices, all chunks (asynchronous) -----------------------
-    for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        const uint64_t n_local = d.f_hi - d.f_lo;
-        if (n_local == 0) continue;
-        CU(cudaSetDevice(d.id));
-        const uint32_t ns = std::max<uint32_t>((d.max_samples + 31u) & ~31u, 32u);
-        const uint32_t cf = (uint32_t)std::min<uint64_t>(chunk_frames, (n_local + 31) & ~31ull);
-        CU(d.planes.reserve((size_t)cf * 2u * ns));
-        CU(d.pcm.reserve(d.pcm_hi - d.pcm_lo + 64));
-        // gaps between tracks (alignment padding) are defined as zero
-        ChunkArgs ca{};
-        ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
-        ca.frame_off = d.frame_off.p; ca.track_shift = d.track_shift.p; ca.planes = d.planes.p;
-        ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo; ca.ns = ns;
-        size_t ev = 4;
-        CU(cudaEventRecord(get_event(d, 3), d.st));
-        for (uint64_t f0 = 0; f0 < n_local; f0 += cf) {
-            ca.f0 = f0;
-            ca.n = (uint32_t)std::min<uint64_t>(cf, n_local - f0);
-            cudaEvent_t a0 = get_event(d, ev), a1 = get_event(d, ev + 1), a2 = get_event(d, ev + 2), a3 = get_event(d, ev + 3);
-            ev += 4;
-            CU(cudaEventRecord(a0, d.st));
-            CU(launch_k1(ca, lanes_for(ctx, ca.n), d.st, &launches));
-            CU(cudaEventRecord(a1, d.st));
-            CU(launch_k2(ca, d.st, &launches));
-            CU(cudaEventRecord(a2, d.st));
-            CU(launch_k3(ca, d.st, &launches));
-            CU(cudaEventRecord(a3, d.st));
-            chunks_total++;
-        }
-        CU(cudaEventRecord(get_event(d, ev), d.st));
-        // alignment gaps between tracks are defined as zero bytes
-        {
-            std::vector<uint64_t> gaps;   // (offset within d.pcm, length) pairs
-            const size_t t0 = track_of(ctx, d.f_lo), t1 = track_of(ctx, d.f_hi - 1);
-            for (size_t t = t0; t < t1; t++) {
-                const uint64_t end = ctx->tracks[t].pcm_off + ctx->tracks[t].pcm_len, nxt = ctx->tracks[t + 1].pcm_off;
-                if (nxt > end && end >= d.pcm_lo) { gaps.push_back(end - d.pcm_lo); gaps.push_back(nxt - end); }
-            }
-            if (d.pcm_first > d.pcm_lo) { gaps.push_back(0); gaps.push_back(d.pcm_first - d.pcm_lo); }
-            for (size_t k = 0; k < gaps.size(); k += 2)
-                CU(cudaMemsetAsync(d.pcm.p + gaps[k], 0, gaps[k + 1], d.st));
-        }
-        // ---- PCM to the caller: the shard is contiguous in the global layout -------
-        if (pcm_dst) {
-            CU(cudaEventRecord(get_event(d, ev + 1), d.st));
-            if (d.pcm_hi > d.pcm_first)
-                CU(cudaMemcpyAsync(pcm_dst + d.pcm_first, d.pcm.p + (d.pcm_first - d.pcm_lo), d.pcm_hi - d.pcm_first,
-                                   cudaMemcpyDeviceToHost, d.st));
-            CU(cudaEventRecord(get_event(d, ev + 2), d.st));
-        }
-        d.decoded = true;
-    }
-    // ---- wait + timings --------------------------------------------------------
-    float k1 = 0, k2 = 0, k3 = 0, kall = 0, d2h = 0;
-    for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        const uint64_t n_local = d.f_hi - d.f_lo;
-        if (n_local == 0) continue;
-        CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.st));
-        const uint32_t ns = std::max<uint32_t>((d.max_samples + 31u) & ~31u, 32u);
-        (void)ns;
-        const uint32_t cf = (uint32_t)std::min<uint64_t>(chunk_frames, (n_local + 31) & ~31ull);
-        size_t ev = 4;
-        float s1 = 0, s2 = 0, s3 = 0, ms = 0;
-        for (uint64_t f0 = 0; f0 < n_local; f0 += cf) {
-            cudaEventElapsedTime(&ms, d.events[ev], d.events[ev + 1]); s1 += ms;
-            cudaEventElapsedTime(&ms, d.events[ev + 1], d.events[ev + 2]); s2 += ms;
-            cudaEventElapsedTime(&ms, d.events[ev + 2], d.events[ev + 3]); s3 += ms;
-            ev += 4;
-        }
-        cudaEventElapsedTime(&ms, d.events[3], d.events[ev]);
-        k1 = std::max(k1, s1); k2 = std::max(k2, s2); k3 = std::max(k3, s3); kall = std::max(kall, ms);
-        if (pcm_dst) { cudaEventElapsedTime(&ms, d.events[ev + 1], d.events[ev + 2]); d2h = std::max(d2h, ms); }
-    }
-    ctx->timing.entropy_ms = k1; ctx->timing.lpc_ms = k2; ctx->timing.stereo_ms = k3;
-    ctx->timing.kernels_ms = kall; ctx->timing.d2h_ms = d2h;
-    ctx->timing.kernel_launches += launches;
-    ctx->timing.chunks = chunks_total;
-    ctx->timing.total_ms = (float)(now_ms() - t_begin);
+    if (pcm_dst && cap < ctx->total_pcm) return fail(ctx, ALACGPU_ERR_CAPACITY, "pcm_dst smaller than the total PCM size");
+    const double t0 = now_ms();
+    int32_t r = build_plan(ctx);
+    if (r) return r;
+    const bool resident = all_resident(ctx);
+    if (!resident) { ctx->timing = alacgpu_timing{}; ctx->index_launches = 0; }
+    // not yet staged: stream mdat in, index and decode chunk by chunk; else decode only
+    uint32_t launches = 0;
+    r = run_pipeline(ctx, !resident, !resident, true, pcm_dst, &launches);
+    if (r) return r;
+    fill_totals(ctx);
+    ctx->timing.kernel_launches = ctx->index_launches + launches;
+    ctx->timing.total_ms = (float)(now_ms() - t0);
     for (size_t t = 0; t < ctx->tracks.size(); t++) {
         if (track_pcm_off) track_pcm_off[t] = ctx->tracks[t].pcm_off;
         if (track_pcm_len) track_pcm_len[t] = ctx->tracks[t].pcm_len;
     }
     if (frame_status) {
-        for (int g = 0; g < n_dev; g++) {
-            Device &d = ctx->devs[g];
+        for (Device &d : ctx->devs) {
             const uint64_t n_local = d.f_hi - d.f_lo;
             if (!n_local) continue;
             CU(cudaSetDevice(d.id));
@@ -645,32 +763,19 @@ int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uin
 }
 
 // ---------------------------------------------------------------------------
-static int32_t ensure_frame_tables(alacgpu_ctx *ctx)
+static int32_t ensure_status(alacgpu_ctx *ctx)
 {
-    if (ctx->have_frame_tables) return ALACGPU_OK;
-    const uint64_t n_frames = ctx->sizes.size();
-    ctx->h_frame_off.assign(n_frames, 0);
-    ctx->h_frame_len.assign(n_frames, 0);
-    ctx->h_status.assign(n_frames, 0);
+    if (ctx->have_status) return ALACGPU_OK;
+    ctx->h_status.assign(ctx->sizes.size(), 0);
     for (Device &d : ctx->devs) {
         const uint64_t n_local = d.f_hi - d.f_lo;
         if (!n_local) continue;
         CU(cudaSetDevice(d.id));
-        std::vector<uint64_t> sh(ctx->tracks.size());
-        CU(cudaMemcpy(ctx->h_frame_off.data() + d.f_lo, d.frame_off.p, n_local * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(ctx->h_frame_len.data() + d.f_lo, d.out_len.p, n_local * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(sh.data(), d.track_shift.p, sh.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
         std::vector<FrameDesc> h(n_local);
         CU(cudaMemcpy(h.data(), d.desc.p, n_local * sizeof(FrameDesc), cudaMemcpyDeviceToHost));
-        size_t t = track_of(ctx, d.f_lo);
-        for (uint64_t i = 0; i < n_local; i++) {
-            const uint64_t gidx = d.f_lo + i;
-            while (t + 1 < ctx->tracks.size() && gidx >= ctx->tracks[t].first_frame + ctx->tracks[t].n_frames) t++;
-            ctx->h_frame_off[gidx] += sh[t];
-            ctx->h_status[gidx] = h[i].status;
-        }
+        for (uint64_t i = 0; i < n_local; i++) ctx->h_status[d.f_lo + i] = h[i].status;
     }
-    ctx->have_frame_tables = true;
+    ctx->have_status = true;
     return ALACGPU_OK;
 }
 
@@ -689,17 +794,13 @@ int32_t alacgpu_read_frame(alacgpu_ctx *ctx, int32_t track, uint32_t frame_idx, 
     *bytes_out = 0;
     const HostTrack &ht = ctx->tracks[track];
     if (frame_idx >= ht.n_frames) return ALACGPU_OK;          // AlacContext.cs:182-186: return 0
-    bool decoded = ctx->prepared;
-    for (Device &d : ctx->devs) if (d.f_hi > d.f_lo && !d.decoded) decoded = false;
-    if (!decoded) {
+    if (!all_decoded(ctx)) {
         r = alacgpu_decode_all(ctx, nullptr, 0, nullptr, nullptr, nullptr);
         if (r) return r;
     }
-    r = ensure_frame_tables(ctx);
-    if (r) return r;
     const uint64_t gidx = ht.first_frame + frame_idx;
-    const uint64_t off = ctx->h_frame_off[gidx];
-    const uint32_t len = ctx->h_frame_len[gidx];
+    const uint64_t off = ctx->frame_off[gidx];
+    const uint32_t len = ctx->out_len[gidx];
     if (len == 0) return ALACGPU_OK;
     if (!dst || cap < len) return fail(ctx, ALACGPU_ERR_CAPACITY, "frame does not fit the destination");
     if (!(off >= ctx->win_lo && off + len <= ctx->win_hi)) {
@@ -740,12 +841,9 @@ int32_t alacgpu_frame_samples(alacgpu_ctx *ctx, int32_t track, uint32_t frame_id
     int32_t r = check_track(ctx, track);
     if (r) return r;
     if (!n_samples) return ALACGPU_ERR_INVALID_ARG;
-    if (!ctx->prepared) return fail(ctx, ALACGPU_ERR_STATE, "alacgpu_prepare has not run");
     const HostTrack &ht = ctx->tracks[track];
     if (frame_idx >= ht.n_frames) return fail(ctx, ALACGPU_ERR_RANGE, "frame index out of range");
-    r = ensure_frame_tables(ctx);
-    if (r) return r;
-    *n_samples = ctx->h_frame_len[ht.first_frame + frame_idx] / (uint32_t)((ht.cfg.sample_size / 8) * ht.cfg.num_channels);
+    *n_samples = ctx->out_len[ht.first_frame + frame_idx] / (uint32_t)((ht.cfg.sample_size / 8) * ht.cfg.num_channels);
     return ALACGPU_OK;
 }
 
@@ -754,11 +852,10 @@ int32_t alacgpu_frame_status(alacgpu_ctx *ctx, int32_t track, uint32_t frame_idx
     int32_t r = check_track(ctx, track);
     if (r) return r;
     if (!status) return ALACGPU_ERR_INVALID_ARG;
-    if (!ctx->prepared) return fail(ctx, ALACGPU_ERR_STATE, "alacgpu_prepare has not run");
     const HostTrack &ht = ctx->tracks[track];
     if (frame_idx >= ht.n_frames) return fail(ctx, ALACGPU_ERR_RANGE, "frame index out of range");
-    ctx->have_frame_tables = false;      // statuses may have changed since the last decode
-    r = ensure_frame_tables(ctx);
+    if (!all_decoded(ctx)) return fail(ctx, ALACGPU_ERR_STATE, "frames have not been decoded yet");
+    r = ensure_status(ctx);
     if (r) return r;
     *status = ctx->h_status[ht.first_frame + frame_idx];
     return ALACGPU_OK;
@@ -768,7 +865,6 @@ int32_t alacgpu_track_pcm_bytes(alacgpu_ctx *ctx, int32_t track, uint64_t *off, 
 {
     int32_t r = check_track(ctx, track);
     if (r) return r;
-    if (!ctx->prepared) return fail(ctx, ALACGPU_ERR_STATE, "alacgpu_prepare has not run");
     if (off) *off = ctx->tracks[track].pcm_off;
     if (len) *len = ctx->tracks[track].pcm_len;
     return ALACGPU_OK;
@@ -799,16 +895,18 @@ int32_t alacgpu_pcm_checksum(alacgpu_ctx *ctx, uint64_t off, uint64_t len, uint6
     for (Device &d : ctx->devs) {
         if (d.f_hi == d.f_lo) continue;
         if (!d.decoded) return fail(ctx, ALACGPU_ERR_STATE, "no decoded PCM on this device");
-        // intersection of [off, off+len) with this shard, on 8-byte word boundaries of the global layout
-        uint64_t lo = std::max(off, d.pcm_lo), hi = std::min(off + len, d.pcm_hi);
+        // this shard's bytes inside [off, off+len); shards start on 256-byte boundaries of the
+        // global layout except where a track is split between devices (then on a frame boundary)
+        uint64_t lo = std::max(off, d.pcm_first), hi = std::min(off + len, d.pcm_hi);
         if (hi <= lo) continue;
         if (lo & 7) return fail(ctx, ALACGPU_ERR_INVALID_ARG, "checksum range must start on an 8-byte boundary of each shard");
         CU(cudaSetDevice(d.id));
-        CU(cudaMemsetAsync(d.scalars.p + 2, 0, sizeof(uint64_t), d.st));
-        CU(launch_checksum(d.pcm.p + (lo - d.pcm_lo), lo, hi - lo, d.scalars.p + 2, d.st));
+        cudaStream_t st = d.slots[0].st;
+        CU(cudaMemsetAsync(d.scalars.p + 2, 0, sizeof(uint64_t), st));
+        CU(launch_checksum(d.pcm.p + (lo - d.pcm_lo), lo, hi - lo, d.scalars.p + 2, st));
         uint64_t part = 0;
-        CU(cudaMemcpyAsync(&part, d.scalars.p + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, d.st));
-        CU(cudaStreamSynchronize(d.st));
+        CU(cudaMemcpyAsync(&part, d.scalars.p + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         total += part;
     }
     *sum = total;

@@ -115,7 +115,14 @@ class BatchDecoder:
         self.n_frames = 0
 
     # -- decode ------------------------------------------------------------------
+    def total_pcm_bytes(self) -> int:
+        total = C.c_uint64(0)
+        self._check(self._L.alacgpu_total_pcm_bytes(self._h, C.byref(total)), "alacgpu_total_pcm_bytes")
+        self.total_pcm = total.value
+        return total.value
+
     def prepare(self) -> int:
+        """Optional: stage every track's mdat in HBM and run the header pre-pass."""
         total = C.c_uint64(0)
         self._check(self._L.alacgpu_prepare(self._h, C.byref(total)), "alacgpu_prepare")
         self.total_pcm = total.value
@@ -132,7 +139,7 @@ class BatchDecoder:
     def decode_all(self, dst=None, want_status: bool = True):
         """dst: None (allocate numpy), a PinnedBuffer / numpy array, or False to keep
         the PCM device-resident.  -> (dst array or None, track_off, track_len, status)."""
-        total = self.prepare()
+        total = self.total_pcm_bytes()
         nt = self.track_count()
         off = np.zeros(max(1, nt), dtype=np.uint64)
         ln = np.zeros(max(1, nt), dtype=np.uint64)

@@ -232,7 +232,7 @@ def run_ours(args):
     dec = BatchDecoder(devices=[local], chunk_frames=args.chunk_frames, entropy_lanes=args.entropy_lanes)
     for t, pb in zip(tracks, pinned):
         dec.add_track(t.cfg, pb, t.stsz)
-    total = dec.prepare()
+    total = dec.prepare()              # stage the mdat in HBM + header pre-pass: inputs resident
     host_out = PinnedBuffer(total)
 
     # ---- parity in the same run: full PCM vs the encoder's input + checksum ----

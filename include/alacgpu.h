@@ -119,12 +119,12 @@ typedef struct alacgpu_track_cfg {
 /* Device-side timings of the last alacgpu_decode_all, from CUDA events
  * recorded on the streams the kernels were launched on. */
 typedef struct alacgpu_timing {
-    float index_ms;        /* K0 header parse + offset scan (alacgpu_prepare)   */
+    float index_ms;        /* K0 header pre-pass, summed over chunks             */
     float entropy_ms;      /* K1, summed over chunks                             */
     float lpc_ms;          /* K2                                                 */
     float stereo_ms;       /* K3                                                 */
-    float kernels_ms;      /* first K1 launch -> last K3 completion              */
-    float h2d_ms;          /* mdat staging copies (add_track)                    */
+    float kernels_ms;      /* device pipeline span: first launch -> last kernel done (includes waits for H2D when streaming) */
+    float h2d_ms;          /* mdat staging copies: first copy issued -> last done */
     float d2h_ms;          /* PCM copies to the caller's buffer                  */
     float total_ms;        /* decode_all wall clock (host)                       */
     uint32_t kernel_launches;  /* kernels launched by the last prepare+decode_all */
@@ -149,8 +149,10 @@ ALACGPU_API int32_t alacgpu_destroy(alacgpu_ctx *ctx);
  * intermediate bounce); frame i occupies frame_sizes[i] bytes starting at
  * first_frame_offset + sum(frame_sizes[0..i)) -- the reference's sequential
  * addressing (AlacContext.cs:194-195).  Frames that extend past mdat_len are
- * truncated (short read, MyStream.cs:47-52).  The copy to HBM is asynchronous;
- * `mdat` must stay valid until alacgpu_prepare returns. */
+ * truncated (short read, MyStream.cs:47-52).  Only the frame headers are
+ * looked at during this call; the bytes are copied to HBM by alacgpu_prepare or
+ * by the first alacgpu_decode_all, so `mdat` must stay valid until that call
+ * returns (frame_sizes is copied immediately). */
 ALACGPU_API int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg,
                                       const uint8_t *mdat, uint64_t mdat_len,
                                       uint64_t first_frame_offset,
@@ -160,15 +162,22 @@ ALACGPU_API int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg 
 ALACGPU_API int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx);
 
 /* ---- decode --------------------------------------------------------------- */
-/* Build the device frame index (header pre-pass + offset scan) for the tracks
- * added so far and report the PCM bytes decode_all will produce.  Track t's
- * PCM starts at a 256-byte aligned offset; *total_pcm_bytes is the size of the
- * buffer decode_all needs (offsets included). */
+/* Size of the buffer alacgpu_decode_all needs for the tracks added so far.
+ * Known as soon as the tracks are added: the host reads the first seven bytes
+ * of every frame (element tag, hassize flag, 32-bit sample count --
+ * AlacFile.cs:435-453) while building its frame index.  Track t's PCM starts at
+ * a 256-byte aligned offset; the total includes those gaps (zero bytes). */
+ALACGPU_API int32_t alacgpu_total_pcm_bytes(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes);
+
+/* OPTIONAL staging step: copy every added track's mdat into HBM and run the
+ * header pre-pass (K0), so that a following alacgpu_decode_all starts from
+ * resident inputs.  Without it alacgpu_decode_all streams the mdat in itself,
+ * chunk by chunk, overlapped with the kernels and the PCM copies. */
 ALACGPU_API int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes);
 
-/* Re-run only the device side of alacgpu_prepare (header pre-pass + offset
- * scan) over the bytes already resident in HBM; no host->device copy.  Used to
- * time the whole kernel path with resident inputs. */
+/* Re-run only the device side of alacgpu_prepare (the header pre-pass) over the
+ * bytes already resident in HBM; no host->device copy.  Used to time the whole
+ * kernel path with resident inputs. */
 ALACGPU_API int32_t alacgpu_reindex(alacgpu_ctx *ctx);
 
 /* Decode every frame of every track.  pcm_dst: caller-owned HOST buffer of
@@ -176,7 +185,10 @@ ALACGPU_API int32_t alacgpu_reindex(alacgpu_ctx *ctx);
  * alacgpu_device_pcm).  track_pcm_off / track_pcm_len (n_tracks entries each,
  * optional) receive where each track's interleaved little-endian PCM landed;
  * frame_status (one int32 per frame, track-major, optional) receives the
- * ALACGPU_FRAME_* codes.  Calls alacgpu_prepare if it has not run. */
+ * ALACGPU_FRAME_* codes.  If the tracks are not resident yet (no
+ * alacgpu_prepare) the call runs the whole pipeline: pinned/pageable H2D of
+ * each chunk's mdat -> K0 -> K1 -> K2 -> K3 -> D2H of the chunk's PCM, with
+ * up to 8 chunks in flight on separate CUDA streams. */
 ALACGPU_API int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap,
                                        uint64_t *track_pcm_off, uint64_t *track_pcm_len,
                                        int32_t *frame_status);
