@@ -49,8 +49,10 @@ def build_host(force: bool = False) -> str:
     deps = srcs + [os.path.join(HOST, h) for h in os.listdir(HOST) if h.endswith((".h", ".hpp"))]
     deps.append(os.path.join(ROOT, "include", "alacgpu.h"))
     if force or _newer(LIB_HOST, deps):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"),
-               "-o", LIB_HOST, *srcs, "-ldl", "-lpthread"]
+        # links against libalacgpu.so next to it (rpath $ORIGIN): the mirror has no decode code of its own
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-fvisibility=hidden",
+               "-I", os.path.join(ROOT, "include"), "-o", LIB_HOST, *srcs,
+               "-L", HERE, "-lalacgpu", "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread"]
         subprocess.check_call(cmd)
     return LIB_HOST
 

@@ -5,12 +5,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _decode(tracks, **kw):
+def _decode(tracks, dst=None, **kw):
     from alac.net_b200 import BatchDecoder
     with BatchDecoder(**kw) as dec:
         for t in tracks:
             dec.add_track(t.cfg, t.mdat, t.stsz)
-        pcm, off, ln, status = dec.decode_all()
+        pcm, off, ln, status = dec.decode_all(dst)
         timing = dec.timing()
         return [pcm[int(o):int(o + l)].tobytes() for o, l in zip(off, ln)], status, timing
 
@@ -19,19 +19,217 @@ def _oracle(oracle, t):
     return oracle.decode_track(oracle.cfg_from(t.cfg), t.mdat, t.stsz)
 
 
-@pytest.mark.parametrize("k,scale", [(1, 0.1), (2, 0.02), (3, 0.2)])
-def test_configs_small(k, scale, gen, oracle):
-    tracks = gen.make_config(k, scale=scale)
-    got, status, timing = _decode(tracks)
+def _assert_tracks_equal(tracks, got, status, oracle, check_encoder=True):
     pos = 0
-    for t, g in zip(tracks, got):
+    for i, (t, g) in enumerate(zip(tracks, got)):
         ref, st, fb = _oracle(oracle, t)
-        assert ref == t.pcm, "oracle does not reproduce the encoder's input"
-        assert np.array_equal(status[pos:pos + t.n_frames], st)
+        if check_encoder:
+            assert ref == t.pcm, "oracle does not reproduce the encoder's input"
+        assert np.array_equal(status[pos:pos + t.n_frames], st), (status[pos:pos + t.n_frames], st)
         assert len(g) == len(ref)
         if g != ref:
             a, b = np.frombuffer(g, np.uint8), np.frombuffer(ref, np.uint8)
             bad = np.nonzero(a != b)[0]
-            raise AssertionError(f"config {k}: {bad.size} bytes differ, first at {bad[:8]}")
+            raise AssertionError(f"track {i}: {bad.size} bytes differ, first at {bad[:8]}")
         pos += t.n_frames
+
+
+@pytest.mark.parametrize("k,scale", [(1, 0.1), (2, 0.02), (3, 0.2)])
+def test_configs_small(k, scale, gen, oracle):
+    tracks = gen.make_config(k, scale=scale)
+    got, status, timing = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle)
     assert timing["kernel_launches"] > 0
+
+
+def test_config1_full_size(gen, oracle):
+    """configs[0] at its full 60 s: 646 frames, last one partial (hassize)"""
+    tracks = gen.make_config(1, scale=1.0)
+    assert tracks[0].n_frames == 646 and tracks[0].frame_samples[-1] == 4080
+    got, status, _ = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle)
+
+
+def test_config3_full_size_divergence(gen, oracle):
+    tracks = gen.make_config(3, scale=1.0)
+    got, status, _ = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle)
+
+
+def test_config4_and_5_shaped_batches(gen, oracle):
+    """many tracks in one decode_all: 16-bit stereo batch (config 4) and the 16/24 mono/stereo mix (config 5)"""
+    tracks = gen.make_config(4, scale=0.004, n_tracks=24) + gen.make_config(5, scale=0.004, n_tracks=20)
+    got, status, _ = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle)
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("chunk", [32, 96, 0])
+def test_chunking_and_lane_options_do_not_change_bytes(lanes, chunk, gen, oracle):
+    tracks = gen.make_config(2, scale=0.01) + gen.make_config(3, scale=0.05)
+    got, status, _ = _decode(tracks, chunk_frames=chunk, entropy_lanes=lanes)
+    _assert_tracks_equal(tracks, got, status, oracle)
+
+
+def test_resident_path_equals_streaming_path(gen, oracle):
+    """prepare() + decode_all (inputs resident) vs decode_all alone (streams H2D chunk by chunk)"""
+    from alac.net_b200 import BatchDecoder, host_checksum
+    tracks = gen.make_config(2, scale=0.01)
+    ref = _oracle(oracle, tracks[0])[0]
+    with BatchDecoder(devices=[0]) as dec:
+        dec.add_track(tracks[0].cfg, tracks[0].mdat, tracks[0].stsz)
+        total = dec.prepare()
+        assert total == len(ref)
+        a = dec.decode_all()[0].tobytes()
+        dec.reindex()
+        dec.decode_all(False, want_status=False)          # device-resident
+        assert dec.checksum() == host_checksum(ref)
+        b = dec.decode_all()[0].tobytes()
+    assert a == ref and b == ref
+
+
+def test_read_frame_is_one_alaccontext_read(gen, oracle):
+    from alac.net_b200 import BatchDecoder
+    t = gen.make_config(1, scale=0.05)[0]
+    ref, st, fbytes = _oracle(oracle, t)
+    with BatchDecoder(devices=[0]) as dec:
+        tid = dec.add_track(t.cfg, t.mdat, t.stsz)
+        assert dec.frame_count(tid) == t.n_frames
+        pos = 0
+        for f in range(t.n_frames):
+            b = dec.read_frame(tid, f)
+            assert len(b) == int(fbytes[f]) and b == ref[pos:pos + len(b)]
+            assert dec.frame_samples(tid, f) == int(t.frame_samples[f])
+            assert dec.frame_status(tid, f) == 0
+            pos += len(b)
+        assert dec.read_frame(tid, t.n_frames) == b""          # past the end: 0 bytes (AlacContext.cs:182-186)
+        assert pos == len(ref)
+
+
+def test_empty_and_ragged_inputs(gen, oracle):
+    from alac.net_b200 import BatchDecoder
+    t = gen.make_config(1, scale=0.02)[0]
+    ref = _oracle(oracle, t)[0]
+    with BatchDecoder(devices=[0]) as dec:
+        out, off, ln, status = dec.decode_all()                # no tracks at all
+        assert ln.size == 0
+        dec.add_track(t.cfg, b"", np.zeros(0, np.uint32))      # a track with no frames
+        dec.add_track(t.cfg, t.mdat, t.stsz)
+        dec.add_track(t.cfg, b"", np.zeros(0, np.uint32))
+        out, off, ln, status = dec.decode_all()
+        assert list(ln) == [0, len(ref), 0]
+        assert out[int(off[1]):int(off[1] + ln[1])].tobytes() == ref
+
+
+def test_truncated_and_malformed_frames_follow_the_oracle_policy(gen, oracle):
+    """stsz pointing past the mdat (short read), zero-length frames, bad tags, garbage bits"""
+    rng = np.random.default_rng(11)
+    t = gen.make_config(1, scale=0.03)[0]
+    # (a) mdat cut in the middle of a frame
+    cut = int(np.cumsum(t.stsz)[t.n_frames // 2] - 100)
+    ta = gen.Track(t.cfg, t.mdat[:cut], t.stsz, t.frame_samples, b"")
+    # (b) random garbage frames of assorted sizes incl. 0 and 1 byte
+    sizes = np.array([0, 1, 2, 7, 64, 300, 2000, 0, 9000], dtype=np.uint32)
+    garbage = rng.integers(0, 256, size=int(sizes.sum()), dtype=np.uint8)
+    garbage[0 if sizes[0] else 1] &= 0x3F       # keep a few tags valid so the entropy kernel runs on noise
+    tb = gen.Track(t.cfg, garbage.tobytes(), sizes, np.zeros(sizes.size, np.int32), b"")
+    # (c) valid frames whose element tag is flipped to 2..7
+    md = bytearray(t.mdat)
+    offs = np.concatenate([[0], np.cumsum(t.stsz.astype(np.int64))])
+    for f in range(0, t.n_frames, 3):
+        md[offs[f]] = (md[offs[f]] & 0x1F) | (int(rng.integers(2, 8)) << 5)
+    tc = gen.Track(t.cfg, bytes(md), t.stsz, t.frame_samples, b"")
+    tracks = [ta, tb, tc]
+    got, status, _ = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
+    assert (status != 0).any()
+
+
+def test_kmodifier_and_history_cookie_variants(gen, oracle):
+    """non-default cookie parameters, incl. k above 16 (two-part Readbits) and tiny kmodifier"""
+    rng = np.random.default_rng(21)
+    tracks = []
+    for kmod, hm, ih in ((14, 40, 10), (6, 63, 200), (20, 40, 10), (2, 20, 0), (23, 255, 255)):
+        cfg = gen.TrackCfg(16, 2, 1024, hm, ih, kmod, 44100)
+        n = 1024 * 6 + 100
+        x = gen.make_signal(int(rng.integers(1, 1 << 30)), n, 16, 44100, 2).copy()
+        x[:, ::5] = rng.integers(-32768, 32768, size=x[:, ::5].shape)
+        fr = gen.make_frames(rng, cfg, n, True, orders=(0, 31), quants=(0, 15), rice_mods=(0, 7), auto_escape=False)
+        tracks.append(gen.build_track(cfg, x, fr))
+    got, status, _ = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle)
+
+
+def test_container_channel_mismatch(gen, oracle):
+    """mono elements in a 2-channel container (zero-filled right) and stereo elements in a
+    1-channel container (left only) -- AlacFile.cs:534-540, :353-354"""
+    rng = np.random.default_rng(31)
+    tracks = []
+    for ss in (16, 24):
+        for cch, stereo in ((2, False), (1, True)):
+            cfg = gen.TrackCfg(ss, cch, 4096, 40, 10, 14, 44100)
+            n = 4096 * 3 + 77
+            x = gen.make_signal(int(rng.integers(1, 1 << 30)), n, ss, 44100, 2 if stereo else 1, wasted_spans=(ss == 24))
+            fr = gen.make_frames(rng, cfg, n, stereo, escape_prob=0.25)
+            if ss == 24:
+                gen.assign_wasted_bytes(fr, x, 24, rng)
+            tracks.append(gen.build_track(cfg, x, fr))
+    got, status, _ = _decode(tracks)
+    _assert_tracks_equal(tracks, got, status, oracle)
+
+
+def test_unsupported_parameters_fail_loudly(gen):
+    from alac.net_b200 import BatchDecoder, AlacGpuError
+    with BatchDecoder(devices=[0]) as dec:
+        for ss, ch in ((20, 2), (32, 2), (8, 1), (16, 3)):
+            with pytest.raises(AlacGpuError) as e:
+                dec.add_track(gen.TrackCfg(ss, ch, 4096, 40, 10, 14, 44100), b"\0" * 8, np.array([8], np.uint32))
+            assert e.value.code == -5
+        t = gen.make_config(1, scale=0.01)[0]
+        dec.add_track(t.cfg, t.mdat, t.stsz)
+        small = np.zeros(16, dtype=np.uint8)
+        with pytest.raises(AlacGpuError) as e:
+            dec.decode_all(small)
+        assert e.value.code == -6
+
+
+def test_full_size_roundtrip_properties_config2(gen):
+    """BASELINE config 2 at full size (14,063 frames, 345.6 MB PCM): the oracle would take a while,
+    so check size-independent properties: decode(encode(pcm)) == pcm, and the device checksum of the
+    resident PCM equals the checksum of the bytes copied to the host (a checksum of checksums over
+    two disjoint halves equals the whole)."""
+    from alac.net_b200 import BatchDecoder, host_checksum
+    t = gen.make_config(2, scale=1.0)[0]
+    assert t.n_frames == 14063 and len(t.pcm) == 345_600_000
+    with BatchDecoder(devices=[0]) as dec:
+        dec.add_track(t.cfg, t.mdat, t.stsz)
+        out, off, ln, status = dec.decode_all()
+        assert (status == 0).all()
+        assert out[:int(ln[0])].tobytes() == t.pcm
+        half = (len(t.pcm) // 2) & ~7
+        whole = dec.checksum()
+        assert whole == host_checksum(out[:int(ln[0])])
+        assert (dec.checksum(0, half) + dec.checksum(half, len(t.pcm) - half)) % (1 << 64) == whole
+
+
+def test_virtual_device_partition_stitches(gen, oracle):
+    """the multi-GPU plan on one GPU: decode each shard of a 4-way partition separately and stitch"""
+    from alac.net_b200 import BatchDecoder
+    from alac.net_b200.shard import rank_slices
+    tracks = gen.make_config(1, scale=0.1) + gen.make_config(3, scale=0.1)
+    refs = [_oracle(oracle, t)[0] for t in tracks]
+    pieces = {i: [] for i in range(len(tracks))}
+    for r in range(4):
+        sl = rank_slices([t.stsz for t in tracks], 4, r)
+        if not sl:
+            continue
+        with BatchDecoder(devices=[0]) as dec:
+            for s in sl:
+                t = tracks[s.track]
+                dec.add_track(t.cfg, t.mdat[s.byte_lo:s.byte_hi], t.stsz[s.frame_lo:s.frame_hi])
+            out, off, ln, status = dec.decode_all()
+            assert (status == 0).all()
+            for s, o, l in zip(sl, off, ln):
+                pieces[s.track].append((s.frame_lo, out[int(o):int(o + l)].tobytes()))
+    for i, ref in enumerate(refs):
+        assert b"".join(p for _, p in sorted(pieces[i])) == ref

@@ -1,0 +1,187 @@
+"""CPU: the C-ABI library loads and exports what include/alacgpu.h declares; pure host
+logic (partition plan, rank sharding under gloo, container grammar of the C++ mirror,
+the synthetic muxer).  No compute call is made here -- there is no GPU and no CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from alac.net_b200 import build
+    build.build_all()
+    return build
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "alacgpu.h")).read()
+    return sorted(set(re.findall(r"ALACGPU_API\s+[\w\s\*]+?\b(alacgpu_\w+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported(built):
+    from alac.net_b200 import _native as N
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    assert sorted(N.EXPORTS) == declared, "ctypes binding and header disagree"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", N.LIB_PATH], text=True)
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"libalacgpu.so does not export {missing}"
+    stray = [s for s in exported if not s.startswith("alacgpu_")]
+    assert not stray, f"non-ABI symbols leak out of libalacgpu.so: {stray[:5]}"
+
+
+def test_library_loads_and_answers_without_a_gpu(built):
+    from alac.net_b200 import _native as N
+    L = N.load()
+    assert L.alacgpu_abi_version() == 1
+    assert L.alacgpu_strerror(0) == b"ok"
+    assert b"no CPU fallback" in L.alacgpu_strerror(N.ERR_NAMES and -2)
+    n = C.c_int32(-1)
+    assert L.alacgpu_device_count(C.byref(n)) == 0
+    if n.value == 0:      # this container: creating a context must fail loudly, never fall back
+        h = C.c_void_p()
+        assert L.alacgpu_create(None, 0, None, C.byref(h)) == -2
+        assert not h.value
+        from alac.net_b200 import BatchDecoder, AlacGpuError
+        with pytest.raises(AlacGpuError):
+            BatchDecoder()
+
+
+def test_product_never_touches_the_oracle():
+    """the product tree must not import / link / mention the oracle or the Python model"""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "alac")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"(from|import)\s+(oracle|pymodel)|alac_oracle|libalac_oracle", src):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_plan_partition_properties(built):
+    from alac.net_b200 import plan_partition
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(100, 25000, size=10007).astype(np.uint32)
+    total = int(sizes.sum())
+    for parts in (1, 2, 3, 4, 8):
+        cut = plan_partition(sizes, parts)
+        assert cut[0] == 0 and cut[-1] == sizes.size and np.all(np.diff(cut.astype(np.int64)) >= 0)
+        loads = [int(sizes[int(a):int(b)].sum()) for a, b in zip(cut[:-1], cut[1:])]
+        assert sum(loads) == total
+        assert max(loads) - min(loads) <= 2 * 25000, loads            # balanced to within a frame or two
+    # degenerate inputs
+    assert list(plan_partition(np.zeros(0, np.uint32), 4)) == [0, 0, 0, 0, 0]
+    assert list(plan_partition(np.array([5], np.uint32), 4))[-1] == 1
+    cut = plan_partition(np.array([1, 1, 1000000, 1, 1], np.uint32), 2)
+    assert 0 <= cut[1] <= 5
+
+
+def test_rank_slices_cover_every_frame_once(built):
+    from alac.net_b200.shard import rank_slices
+    rng = np.random.default_rng(4)
+    tracks = [rng.integers(50, 9000, size=n).astype(np.uint32) for n in (17, 1, 300, 0, 45)]
+    for world in (1, 2, 4, 8):
+        seen = [np.zeros(t.size, dtype=np.int32) for t in tracks]
+        for r in range(world):
+            for s in rank_slices(tracks, world, r):
+                seen[s.track][s.frame_lo:s.frame_hi] += 1
+                offs = np.concatenate([[0], np.cumsum(tracks[s.track].astype(np.int64))])
+                assert (s.byte_lo, s.byte_hi) == (offs[s.frame_lo], offs[s.frame_hi])
+        assert all((x == 1).all() for x in seen)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from alac.net_b200.shard import rank_slices, reduce_step
+from oracle import oracle as O            # checker only (this is a test)
+from tools.alacgen import alacgen as G
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+tracks = [G.make_config(1, scale=0.02)[0], G.make_config(3, scale=0.03)[0]]
+whole = [O.decode_track(O.cfg_from(t.cfg), t.mdat, t.stsz)[0] for t in tracks]
+# each rank decodes ONLY its frame ranges (stand-in for its GPU), then the shards are stitched
+mine = []
+for s in rank_slices([t.stsz for t in tracks], world, rank):
+    t = tracks[s.track]
+    pcm, st, fb = O.decode_track(O.cfg_from(t.cfg), t.mdat[s.byte_lo:s.byte_hi], t.stsz[s.frame_lo:s.frame_hi])
+    mine.append((s.track, s.frame_lo, pcm))
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+ms, units = reduce_step(dist, "cpu", 10.0 + rank, float(sum(len(p) for _, _, p in mine)))
+if rank == 0:
+    parts = sorted((x for g in gathered for x in g), key=lambda x: (x[0], x[1]))
+    for ti in range(len(tracks)):
+        stitched = b"".join(p for t, _, p in parts if t == ti)
+        assert stitched == whole[ti] == tracks[ti].pcm, "stitched shards differ from the whole-track decode"
+    assert ms == 10.0 + world - 1 and units == float(sum(len(w) for w in whole))
+    print("GLOO_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_frame_range_sharding_world_size_2_gloo(tmp_path, built, oracle, gen):
+    script = tmp_path / "gloo_worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "GLOO_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- container grammar: the C++ QtMovieT mirror against the synthetic muxer -------------
+def test_demux_tables_match_the_muxer(built, gen):
+    from alac.net_b200 import hostmirror as H
+    for k, scale in ((1, 0.05), (2, 0.005), (3, 0.05)):
+        t = gen.make_config(k, scale=scale)[0]
+        for kw in ({}, {"free_atom": True}):
+            m4a = gen.mux_m4a(t, **kw)
+            d = H.demux(m4a)
+            assert d["status"] == 1                                        # MdatPosStatus.Ok
+            assert (d["sample_size"], d["num_channels"], d["sample_rate"]) == (t.cfg.sample_size, t.cfg.num_channels, t.cfg.sample_rate)
+            assert np.array_equal(d["stsz"], t.stsz)
+            assert m4a[d["mdat_pos"]:d["mdat_pos"] + len(t.mdat)] == t.mdat
+            cd = d["codec_data"]
+            assert int(cd[24]) << 24 | int(cd[25]) << 16 | int(cd[26]) << 8 | int(cd[27]) == t.cfg.max_samples_per_frame
+            assert (cd[30], cd[31], cd[32]) == (t.cfg.rice_history_mult, t.cfg.rice_initial_history, t.cfg.rice_kmodifier)
+
+
+def test_demux_rejections_match_the_reference(built, gen):
+    from alac.net_b200 import hostmirror as H
+    t = gen.make_config(1, scale=0.02)[0]
+    good = gen.mux_m4a(t)
+    # mdat before moov: SetSavedMdat compares Seek()'s returned position with 0 -> CannotSeek (QTMovieT.cs:744-748)
+    assert H.demux(gen.mux_m4a(t, mdat_first=True))["status"] == 3
+    # unknown top-level atom -> None (QTMovieT.cs:103-107)
+    bad = good[:28] + b"\x00\x00\x00\x08wide" + good[28:]
+    assert H.demux(bad)["status"] == 0
+    # truncated before mdat -> EOF -> None
+    assert H.demux(good[:200])["status"] == 0
+    # an extra atom inside stbl (e.g. 'sgpd') is rejected (QTMovieT.cs:221-225)
+    i = good.index(b"stco") - 4
+    broken = bytearray(good)
+    broken[i + 4:i + 8] = b"co64"
+    assert H.demux(bytes(broken))["status"] == 0
+
+
+def test_uniform_stsz(built, gen):
+    from alac.net_b200 import hostmirror as H
+    cfg = gen.TrackCfg(16, 2, 64, 40, 10, 14, 44100)
+    rng = np.random.default_rng(9)
+    x = rng.integers(-30000, 30000, size=(2, 64 * 5)).astype(np.int32)
+    fr = gen.make_frames(rng, cfg, 64 * 5, True, escape_prob=1.0, end_tag=False)
+    t = gen.build_track(cfg, x, fr)
+    assert len(set(t.stsz.tolist())) == 1
+    d = H.demux(gen.mux_m4a(t, uniform_stsz=True))
+    assert d["status"] == 1 and np.array_equal(d["stsz"], t.stsz)
