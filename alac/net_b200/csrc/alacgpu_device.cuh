@@ -11,10 +11,11 @@
 //   FrameDesc[]/FrameCoefs[] : K0's parse of each frame header
 //                (AlacFile.cs:435-475 / :584-641).
 //   planes     : int32 residual / predicted samples of one pipeline chunk,
-//                "tile transposed": tile = 32 consecutive frames,
-//                plane[((tile*2 + ch) * NS + i) * 32 + lane]; a warp whose
-//                lanes are the tile's frames touches one 128-byte line per
-//                sample index i.
+//                stream-major: row (slot*2 + ch) = the NS samples of channel
+//                ch of the chunk's frame `slot`, rows 128-byte aligned and
+//                padded (NS = align32(max N) + 32).  K1 writes a lane's row 8
+//                samples at a time, K2 rewrites it in place 4 at a time, K3
+//                streams 8 sample-frames per thread out of the two rows.
 //   pcm        : interleaved little-endian PCM, frame after frame.
 #pragma once
 

@@ -27,7 +27,8 @@ struct K0Args {
 cudaError_t launch_k0(const K0Args &a, cudaStream_t st, uint32_t *launches);
 
 // One pipeline chunk = frames [f0, f0 + n) of the device's frame list; planes
-// hold ceil(n / 32) tiles of 2 channels x ns samples x 32 lanes int32.
+// are stream-major: row (slot * 2 + ch) holds the ns int32 residual / predicted
+// samples of channel ch of the chunk's frame `slot` (rows 128-byte aligned).
 struct ChunkArgs {
     const uint8_t *arena;
     const FrameRef *refs;
@@ -40,7 +41,10 @@ struct ChunkArgs {
     uint64_t pcm_base;
     uint64_t f0;
     uint32_t n;
-    uint32_t ns;                   // plane stride in samples
+    uint32_t ns;                   // plane row stride in samples (multiple of 32)
+    uint32_t max_sf;               // most sample-frames any frame of the batch emits
+    uint32_t *perm;                // K2 work list: active stream ids sorted by descending order (2n entries)
+    uint32_t *perm_count;          // [0] = number of entries of perm
 };
 cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);

@@ -7,45 +7,52 @@
 // Mapping.  A frame's Rice streams are one serial chain: every symbol's
 // length depends on the running history, and channel B starts at the bit
 // where channel A ends (AlacFile.cs:643 then :653 share one cursor).  So the
-// unit of parallelism is the FRAME: one lane per frame, channel A then B.
-// The loop is written in lock step over the OUTPUT index i -- a lane that is
-// inside a zero run emits its zeros one per iteration instead of jumping
-// ahead (AlacFile.cs:238-245 writes them in a burst) -- so all lanes of a warp
-// are at the same i and the store of sample i is one coalesced 128-byte line
-// of the tile-transposed residual plane.
+// unit of parallelism is the FRAME: one lane per frame, channel A then B, and
+// the kernel's run time is (symbols per frame) x (cycles per symbol) whatever
+// the batch size.  Everything here serves a short per-symbol dependency chain:
 //
-// Bitstream access: each lane walks its own frame through two byte-swapped
-// 32-bit words plus a prefetched third; a 32-bit window at the cursor is one
-// funnel shift, the unary prefix is __clz(~window), and the k extra bits come
-// from the same window (9 + 22 bits at most).  The reference's "read k bits,
-// un-read one if the value is <= 1" (AlacFile.cs:205-210) becomes "consume
-// k-1 bits".  CountLeadingZeros' clz(0)==40 quirk (AlacFile.cs:190) is kept.
+//   * ONE BIT FIELD PER LOOP ITERATION PER LANE, whatever its kind.  The
+//     reference decodes three kinds of field: the sample's Rice symbol, the
+//     zero-run length symbol that follows a small history (:231-249), and the
+//     raw field after nine 1-bits (:198-202).  A lane that hit one of the rare
+//     kinds simply spends an extra iteration on it (two state bits say what
+//     the next field is); the other lanes do not wait for it as they would if
+//     the rare paths were divergent branches.  Lanes therefore drift apart by
+//     a few percent, so each lane writes through its own output counter:
+//     residuals go to a conflict-free shared-memory ring ([slot][lane]) and
+//     leave it as 16-byte stores into the lane's row of the stream-major plane
+//     at warp-uniform flush points (every eight iterations).  A zero run emits
+//     one zero per iteration.
+//   * The loop body is one small straight-line block (it must stay in the
+//     instruction cache: a lone warp per scheduler cannot hide fetch misses).
+//     All state changes are selects; the operands that depend on the field
+//     just read (new cursor, new history) are one or two instructions after it:
+//     the alternatives (skip k or k+1 bits, raw vs Rice value, keep vs update
+//     the history) are computed beside the field extraction and chosen late.
+//   * bitstream: each lane owns a 256-byte ring in shared memory, filled by
+//     16-byte cp.async copies at the flush points (no register ever waits on
+//     HBM); the cursor keeps two byte-swapped words in registers plus one
+//     prefetched word, so the 32-bit window at the cursor is ONE funnel shift.
+//   * unary prefix = bfind(~window); the k extra bits come from the same
+//     window: k <= 22 always ((history >> 9) + 3 < 2^23; zero-run k <= 16), so
+//     prefix + terminator + k bits fit 32.  "Read k bits, un-read one if the
+//     value is <= 1" (AlacFile.cs:205-210) is "consume k-1 bits".
+//   * CountLeadingZeros' clz(0) == 40 quirk (AlacFile.cs:190) is kept in the
+//     zero-run k, the only place a zero argument can reach it.
 //
-// The common path (prefix < 9 ones, history >= 128) is kept free of error
-// checks: the cursor only moves forward, so "some symbol ended past the
-// frame's last bit" is decided once from the final cursor (policy: OVERRUN
-// outranks a later HISTORY / RUN_OVERFLOW fault, exactly as the oracle's
-// per-symbol check does).  The arena carries enough tail padding for a lane
-// that runs past its frame until then.
+// Error policy (shared with the oracle): the cursor only moves forward, so
+// "some symbol ended past the frame's last bit" is decided once from the
+// final cursor (OVERRUN outranks a HISTORY / RUN_OVERFLOW fault).  The arena
+// carries enough tail padding for a lane that runs past its frame.
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
 
 namespace alacgpu {
 
-// Per-lane bitstream ring in shared memory, filled by 16-byte cp.async (LDGSTS) copies:
-// the copy engine writes shared memory directly, so no register ever waits on HBM.  The
-// ring holds kRingChunks x 16 B of the lane's stream.  Once every kPeriod samples the warp
-// tops every lane's ring up to kRingChunks chunks past its cursor (a warp-uniform branch
-// with a short per-lane loop) and waits for the PREVIOUS period's copies; a period is
-// ~1000 cycles, so that wait is normally free.  A lane consumes at most 59 bits per sample
-// (9 ones + 25 raw bits, plus a zero-run symbol of 9 + 16), i.e. < 4 chunks per period, and
-// reads at most one chunk ahead of its cursor: everything it touches during a period lies
-// within cursor_chunk(previous top-up) + 4 + 4 + 1 < kRingChunks and was requested at
-// least one period earlier.  Between top-ups the per-sample path only does one predicated
-// 4-byte LDS when the cursor enters a new word.
-constexpr int kRingChunks = 16;              // 256 B per lane, 32 KB per 128-thread block
-constexpr int kRingWords = kRingChunks * 4;
-constexpr int kPeriod = 8;
+constexpr int kRingChunks = 16;              // 256 B of bitstream per lane
+constexpr int kRingBytes = kRingChunks * 16;
+constexpr int kOutSlots = 16;                // residual ring: 16 slots x 32 lanes x 4 B per warp
+constexpr int kFlushEvery = 8;               // iterations between flush / top-up points
 constexpr int kK1Threads = 128;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr)
@@ -61,177 +68,213 @@ __device__ __forceinline__ uint32_t lds32(uint32_t smem_addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts32(uint32_t smem_addr, int32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
+}
+// position of the most significant 1 bit (31 - clz), -1 for 0
+__device__ __forceinline__ int flo(uint32_t v)
+{
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 
-struct LaneReader {
-    const uint8_t *base;    // 16-byte aligned address of chunk 0
-    uint32_t ring;          // shared-space byte address of this lane's ring
-    uint32_t widx;          // word index (from base) of `cur`
-    uint32_t cur, nxt;      // byte-swapped words widx, widx+1
-    uint32_t nn;            // raw word widx+2, read from the ring one word ahead
+// Bit cursor over the lane's ring.  A lane consumes at most 32 bits per iteration, i.e. at
+// most two 16-byte chunks per flush period, and reads two words ahead of its cursor:
+// everything it touches during a period was requested at least one period earlier, so the
+// wait for the PREVIOUS period's copies is normally free.
+struct BitCursor {
+    const uint8_t *base;    // 16-byte aligned global address of chunk 0
+    uint32_t ring;          // shared-space byte address of this lane's ring (256-byte aligned)
+    uint32_t ra;            // shared-space address of the next word to prefetch into `nn`
+    uint32_t cur, nxt;      // byte-swapped words holding bits [32*w, 32*w+64) at the cursor's word w
+    uint32_t nn;            // raw word w+2
+    uint32_t off;           // cursor bit within `cur`, 0..31
+    uint32_t words;         // words entered since init (cursor word = word0 + words)
+    uint32_t word0, off0;   // cursor at init
     uint32_t filled;        // chunks [0, filled) have been requested
-    int off;                // cursor bit within cur, 0..31
-    uint32_t start_bit;     // cursor position at init, relative to base
 
-    __device__ __forceinline__ uint32_t word_addr(uint32_t w) const { return ring + ((w & (kRingWords - 1)) << 2); }
-
-    // request every chunk up to kRingChunks past the cursor's chunk
     __device__ __forceinline__ void top_up()
     {
-        const uint32_t want = (widx >> 2) + kRingChunks;
+        const uint32_t want = ((word0 + words) >> 2) + kRingChunks;
         while (filled < want) {
             cp_async16(ring + ((filled & (kRingChunks - 1)) << 4), base + ((uint64_t)filled << 4));
             ++filled;
         }
         cp_async_commit();
     }
-
     __device__ __forceinline__ void init(const uint8_t *arena, uint64_t abs_bit, uint32_t ring_addr)
     {
         const uint64_t byte = abs_bit >> 3;
         base = arena + (byte & ~15ull);
         ring = ring_addr;
-        start_bit = (uint32_t)(byte & 15) * 8u + (uint32_t)(abs_bit & 7);
-        widx = start_bit >> 5;
-        off = (int)(start_bit & 31);
+        const uint32_t pos = (uint32_t)(byte & 15) * 8u + (uint32_t)(abs_bit & 7);
+        word0 = pos >> 5;
+        off = off0 = pos & 31;
+        words = 0;
         filled = 0;
         top_up();
         cp_async_wait<0>();
-        cur = bswap32(lds32(word_addr(widx)));
-        nxt = bswap32(lds32(word_addr(widx + 1)));
-        nn = lds32(word_addr(widx + 2));
+        cur = bswap32(lds32(ring + ((word0 * 4u) & (kRingBytes - 1))));
+        nxt = bswap32(lds32(ring + (((word0 + 1) * 4u) & (kRingBytes - 1))));
+        nn = lds32(ring + (((word0 + 2) * 4u) & (kRingBytes - 1)));
+        ra = ring + (((word0 + 3) * 4u) & (kRingBytes - 1));
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, off); }
 
-    // Skip 0 <= n <= 32 bits, branch free: entering a new word is a few selects plus one
-    // predicated LDS.
-    __device__ __forceinline__ void skip(int n)
+    // move the cursor to bit t (0..63) of the current word pair
+    __device__ __forceinline__ void seek(uint32_t t)
     {
-        off += n;
-        const bool rf = off >= 32;
-        off &= 31;
-        widx += rf ? 1u : 0u;
+        const bool rf = t >= 32u;
+        off = t & 31u;
         cur = rf ? nxt : cur;
-        nxt = rf ? bswap32(nn) : nxt;
-        const uint32_t rd = word_addr(widx + 2);
+        // nxt = rf ? bswap(nn) : nxt in one PRMT: selector 0x0123 reverses nn, 0x7654 passes nxt
+        nxt = __byte_perm(nn, nxt, rf ? 0x0123u : 0x7654u);
+        words += rf ? 1u : 0u;
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "setp.ne.u32 p, %1, 0;\n\t"
-            "@p ld.shared.u32 %0, [%2];\n\t"
+            "setp.ne.u32 p, %2, 0;\n\t"
+            "@p ld.shared.u32 %0, [%1];\n\t"
+            "@p add.u32 %1, %1, 4;\n\t"
+            "@p lop3.b32 %1, %1, 255, %3, 0xEA;\n\t"      // (ra & 255) | ring
             "}"
-            : "+r"(nn)
-            : "r"((uint32_t)rf), "r"(rd)
+            : "+r"(nn), "+r"(ra)
+            : "r"((uint32_t)rf), "r"(ring)
             : "memory");
     }
-    // bits consumed since init
-    __device__ __forceinline__ uint32_t consumed() const { return widx * 32u + (uint32_t)off - start_bit; }
+    __device__ __forceinline__ uint32_t consumed() const { return words * 32u + off - off0; }
 };
-
-// Rare path of EntropyDecodeValue: nine 1-bits, then the raw value (AlacFile.cs:198-202).
-__device__ __forceinline__ uint32_t decode_escape(LaneReader &br, int raw_bits)
-{
-    br.skip(9);
-    const uint32_t v = br.peek() >> (32 - raw_bits);
-    br.skip(raw_bits);
-    return v;
-}
-
-// EntropyDecodeValue (AlacFile.cs:193-212) with m = ((1 << k) - 1) & mask, kinv = 32 - k.
-// k == 1 needs no special case: the generic path reads one bit that is always <= 1, gives
-// it back, and multiplies by m == 1.
-__device__ __forceinline__ uint32_t decode_symbol(LaneReader &br, int raw_bits, int k, int kinv, uint32_t m)
-{
-    const uint32_t w = br.peek();
-    const int x = __clz((int)~w);                       // leading 1 bits
-    if (__builtin_expect(x > 8, 0)) return decode_escape(br, raw_bits);
-    const uint32_t e = (w << (x + 1)) >> kinv;          // :205
-    const uint32_t em = max(e, 1u) - 1u;                // :207-208 (e > 1 ? e - 1 : 0)
-    br.skip(x + k + (int)(min(e, 2u) >> 1));            // :210 Unreadbits(1) when e <= 1
-    return (uint32_t)x * m + em;                        // :206
-}
 
 __global__ void __launch_bounds__(kK1Threads)
 k1_entropy(const ChunkArgs a, const int lanes_log2)
 {
-    __shared__ __align__(16) uint32_t ring_smem[kRingWords * kK1Threads];
+    __shared__ __align__(256) uint8_t ring_smem[kRingBytes * kK1Threads];
+    __shared__ int32_t out_smem[(kK1Threads / 32) * kOutSlots * 32];
     const int lane = threadIdx.x & 31;
     const int S = 1 << lanes_log2;
-    if (lane >= S) return;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t slot = gw * (uint32_t)S + (uint32_t)lane;
-    if (slot >= a.n) return;
-    const uint64_t f = a.f0 + slot;
+    // Every lane stays in the loops (their exits are warp votes); a lane without work runs
+    // with n == 0 and commits nothing.
+    bool work = lane < S && slot < a.n;
+    const uint64_t f = a.f0 + (work ? slot : 0u);
     const FrameDesc d = a.desc[f];
-    if (d.status != FS_OK || (d.flags & FF_ESCAPE)) return;   // escape frames are read directly by K3
-
+    work = work && d.status == FS_OK && !(d.flags & FF_ESCAPE);   // escape frames are read directly by K3
     const FrameRef ref = a.refs[f];
     const TrackCfg cfg = a.cfgs[ref.track];
-    const int n = d.n;
+    int n = work ? (int)d.n : 0;
     const int rss = d.rss;
     const int kmod = cfg.rice_kmodifier;
     const uint32_t kmask = (1u << kmod) - 1u;                // AlacFile.cs:483,:643
     const int ech = (d.flags & FF_STEREO) ? 2 : 1;
+    const int ech_max = __reduce_max_sync(0xffffffffu, n ? ech : 0);
 
-    LaneReader br;
-    const uint64_t abs_bit = ref.off * 8ull + d.data_bit;
-    br.init(a.arena, abs_bit, (uint32_t)__cvta_generic_to_shared(ring_smem) + threadIdx.x * (kRingWords * 4u));
+    BitCursor br;
+    br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull,
+            (uint32_t)__cvta_generic_to_shared(ring_smem) + threadIdx.x * (uint32_t)kRingBytes);
+    // residual ring: slot s of this lane at out_ring + s * 128 (bank == lane)
+    const uint32_t out_ring = (uint32_t)__cvta_generic_to_shared(out_smem) +
+                              (uint32_t)(threadIdx.x >> 5) * (kOutSlots * 128u) + (uint32_t)lane * 4u;
 
-    int32_t *plane = a.planes + ((uint64_t)(slot >> 5) * 2u) * a.ns * kTile + (slot & 31);
     uint8_t status = FS_OK;
+    for (int c = 0; c < ech_max; c++) {
+        int4 *row = reinterpret_cast<int4 *>(a.planes + ((uint64_t)(work ? slot : 0u) * 2u + (uint32_t)c) * a.ns);
+        const uint32_t mult = (uint32_t)((int32_t)d.rice_mod[c & 1] * (cfg.rice_history_mult / 4));   // :483
+        int nc = c < ech ? n : 0;                // samples this lane decodes in this channel
+        int cnt = 0;                             // residuals produced so far (== the reference's outputCount)
+        int flushed = 0;                         // residuals already stored to the row
+        int32_t h = cfg.rice_initial_history;    // :216
+        uint32_t sm1 = 0xFFFFFFFFu;              // signModifier - 1
+        uint32_t zcnt = 0;                       // zeros of the current run still to emit
+        bool isz = false;                        // next field belongs to a zero-run length symbol
+        bool rawp = false;                       // next field is the raw value after nine 1 bits
+        int k = min(flo((uint32_t)((h >> 9) + 3)), kmod);        // :221-222
 
-    for (int c = 0; c < ech && status == FS_OK; c++) {
-        int32_t *out = plane + (uint64_t)c * a.ns * kTile;
-        const int32_t mult = (int32_t)d.rice_mod[c] * (cfg.rice_history_mult / 4);   // :483
-        int32_t h = cfg.rice_initial_history;                                         // :216
-        uint32_t sign_mod = 0;
-        uint32_t zrun = 0;
-        int k = min(31 - __clz((h >> 9) + 3), kmod);                                  // :221-222
-        for (int i = 0; i < n; i++) {
-            if ((i & (kPeriod - 1)) == 0) {          // warp-uniform: lanes are in lock step on i
-                br.top_up();
-                cp_async_wait<1>();                   // everything but the group just committed
+        for (;;) {
+            br.top_up();
+            cp_async_wait<1>();                  // everything but the group just committed
+#pragma unroll 1
+            for (int it = 0; it < kFlushEvery; it++) {
+                // ---- what this lane does in this iteration -------------------------------
+                const bool more = cnt < nc;
+                const bool zero = more && zcnt != 0;             // emit one zero of a run
+                const bool act = more && zcnt == 0;              // read one bit field
+                const uint32_t w = br.peek();
+                const int p = flo(~w);                           // bit index of the first 0 bit
+                const bool esc = w >= 0xFF800000u;               // nine 1 bits (:198)
+                const bool rice = act && !rawp && !esc;          // a complete Rice symbol
+                const bool got = act && (rawp || !esc);          // this iteration completes a symbol
+                const bool gotm = got && !isz, gotz = got && isz;
+                const int rb = isz ? 16 : rss;                   // raw field width (:201, :236)
+                // ---- the field --------------------------------------------------------------
+                const uint32_t m0 = rawp ? 0u : (1u << k) - 1u;
+                const uint32_t e = (w >> ((p - k) & 31)) & m0;   // k bits after the terminator (:205)
+                const uint32_t em = max(e, 1u);                  // raw: m0 == 0 -> em == 1
+                const uint32_t mm = isz ? (m0 & kmask) : m0;     // :206 multiplier
+                // A + em = decoded value (+ signModifier for a sample):  Rice x*mm + max(e,1) - 1,
+                // raw field w >> (32 - rb)
+                const uint32_t x = (uint32_t)(31 - p);
+                const uint32_t smz = isz ? 0xFFFFFFFFu : sm1;
+                const uint32_t A = (rawp ? (w >> (32 - rb)) : x * mm) + smz;
+                const uint32_t dv = A + em;
+                // ---- cursor: Rice consumes x + k (+1 if e >= 2) bits (:210), raw rb, escape prefix 9
+                const uint32_t t_rice = br.off + (uint32_t)(31 + k - p);
+                const uint32_t t_else = br.off + (act ? (rawp ? (uint32_t)rb : 9u) : 0u);
+                const uint32_t t = (rice ? t_rice : t_else) + ((rice && e >= 2u) ? 1u : 0u);
+                br.seek(t);
+                // ---- history (:229): samples update it, a run length resets it (:248) -------------
+                const uint32_t mult_e = gotm ? mult : 0u;
+                const int32_t hb = gotz ? 0 : (gotm ? h - ((int32_t)((uint32_t)h * mult) >> 9) : h);
+                const int32_t hn = (int32_t)(em * mult_e + (A * mult_e + (uint32_t)hb));
+                h = (gotm && dv > 0xFFFFu) ? 0xFFFF : hn;
+                // ---- outputs ------------------------------------------------------------------------
+                const int32_t val = (int32_t)(dv >> 1) ^ -(int32_t)(dv & 1u);         // :225-226
+                const bool emit = gotm || zero;
+                if (emit) sts32(out_ring + (((uint32_t)cnt & (kOutSlots - 1)) << 7), zero ? 0 : val);
+                cnt += emit ? 1 : 0;
+                // ---- state ----------------------------------------------------------------------------
+                zcnt = gotz ? dv : zcnt - (zero ? 1u : 0u);                           // :238-245
+                sm1 = gotm ? 0xFFFFFFFFu : (gotz ? (dv > 0xFFFFu ? 0xFFFFFFFFu : 0u) : sm1);   // :227, :233, :246
+                rawp = act && !rawp && esc;
+                const bool toz = gotm && h < 128 && cnt < nc;                         // :231 (cnt is already i + 1)
+                isz = got ? toz : isz;
+                if (__builtin_expect((gotm && h < 0) || (gotz && dv != 0 && (uint32_t)cnt + dv > (uint32_t)kMaxFrameSamples), 0)) {
+                    status = h < 0 ? FS_HISTORY : FS_RUN_OVERFLOW;                    // reference: garbage k / IndexOutOfRange
+                    nc = n = 0;
+                }
+                // ---- k of the next field: :221-222, or :234 for a run length (clz(0) == 40) -------------
+                const int km = min(flo((uint32_t)((h >> 9) + 3)), kmod);
+                const int kz = (h == 0 ? 40 : 31 - flo((uint32_t)h)) + ((h + 16) >> 6) - 24;
+                k = isz ? kz : km;
             }
-            // One basic block for the common case: every lane evaluates the symbol at its
-            // cursor; lanes inside a zero run (dec == false) commit nothing and emit 0.
-            const bool dec = zrun == 0;
-            const uint32_t w = br.peek();
-            const int x = __clz((int)~w);                                             // leading 1 bits
-            const uint32_t e = (w << (x + 1)) >> (32 - k);                            // :205
-            uint32_t v = (uint32_t)x * ((1u << k) - 1u) + (max(e, 1u) - 1u);          // :206-208
-            int adv = x + k + (int)(min(e, 2u) >> 1);                                 // :210
-            if (__builtin_expect(dec && x > 8, 0)) {                                  // :198-202
-                v = decode_escape(br, rss);
-                adv = 0;
-            }
-            br.skip(dec ? adv : 0);
-            const uint32_t dv = v + sign_mod;                                         // :224
-            const int32_t val = dec ? ((int32_t)(dv >> 1) ^ -(int32_t)(dv & 1u)) : 0;  // :225-226
-            const int32_t hn = (int32_t)((uint32_t)h + dv * (uint32_t)mult) - ((int32_t)((uint32_t)h * (uint32_t)mult) >> 9);
-            const int32_t hd = dv > 0xFFFFu ? 0xFFFF : hn;                            // :229
-            h = dec ? hd : h;
-            sign_mod = dec ? 0u : sign_mod;
-            zrun -= dec ? 0u : 1u;                                                    // :240-243, one zero per step
-            if (__builtin_expect(dec && h < 128, 0)) {
-                if (h < 0) { status = FS_HISTORY; break; }
-                if (i + 1 < n) {                                                      // :231
-                    const int kz = (h == 0 ? 40 : __clz(h)) + ((h + 16) >> 6) - 24;   // :234 (clz(0) == 40)
-                    const uint32_t block = decode_symbol(br, 16, kz, 32 - kz, ((1u << kz) - 1u) & kmask);   // :236
-                    if (block > 0 && (uint32_t)i + 1u + block > (uint32_t)kMaxFrameSamples) {
-                        status = FS_RUN_OVERFLOW;                                     // reference: IndexOutOfRange
-                        break;
-                    }
-                    zrun = block;
-                    sign_mod = block > 0xFFFFu ? 0u : 1u;                             // :233,:246
-                    h = 0;                                                            // :248
+            // ---- flush complete groups of four residuals (at most two are pending) -----------------
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (flushed + 4 <= cnt) {
+                    const uint32_t s0 = (uint32_t)flushed & (kOutSlots - 1);
+                    row[flushed >> 2] = make_int4((int32_t)lds32(out_ring + (s0 << 7)), (int32_t)lds32(out_ring + ((s0 + 1) << 7)),
+                                                  (int32_t)lds32(out_ring + ((s0 + 2) << 7)), (int32_t)lds32(out_ring + ((s0 + 3) << 7)));
+                    flushed += 4;
                 }
             }
-            k = min(31 - __clz((h >> 9) + 3), kmod);                                  // :221-222
-            out[(uint32_t)i * kTile] = val;
+            if (__all_sync(0xffffffffu, cnt >= nc)) break;
+        }
+        // tail: the last 1..3 residuals of the channel, zero padded (rows are padded to a multiple of 8)
+        if (flushed < cnt) {
+            int32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                v[j] = flushed + j < cnt ? (int32_t)lds32(out_ring + ((((uint32_t)flushed + j) & (kOutSlots - 1)) << 7)) : 0;
+            row[flushed >> 2] = make_int4(v[0], v[1], v[2], v[3]);
         }
     }
-    // The cursor is monotone: it ended past the frame iff some symbol did.
-    if (d.data_bit + br.consumed() > ref.len * 8u) status = FS_OVERRUN;
-    if (status != FS_OK) a.desc[f].status = status;
+    if (work) {
+        // The cursor is monotone: it ended past the frame iff some symbol did.
+        if (d.data_bit + br.consumed() > ref.len * 8u) status = FS_OVERRUN;
+        if (status != FS_OK) a.desc[f].status = status;
+    }
 }
 
 cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches)

@@ -1,20 +1,23 @@
 // K2 -- adaptive FIR predictor reconstruction (sign-LMS), in place on the
-// residual planes.
+// stream-major residual planes.
 //
 // Replaces PredictorDecompressFirAdapt (ALACDecoder/AlacFile.cs:256-336).
 //
 // Mapping.  The recurrence is serial in the sample index but independent per
-// (frame, channel), and K1 left the residuals tile-transposed, so one LANE
-// owns one channel of one frame and a warp covers the 32 frames of a tile for
-// one channel: sample i of all 32 channel-streams is one 128-byte line, read
-// once and overwritten once.  (A "warp per stream, shuffle-reduce over taps"
-// mapping issues about as many instructions per stream-sample but puts ~6
-// dependent shuffles on every sample's critical path; see DESIGN.md.)
+// (frame, channel) "stream".  One LANE owns one stream and walks its own row
+// of the plane four samples at a time (one 16-byte load and one 16-byte store
+// per four samples, prefetched two blocks ahead).  The work per sample is
+// proportional to the stream's predictor order, and all lanes of a warp
+// execute the warp's largest order, so a pre-pass (k0s_order_sort) sorts the
+// chunk's active streams by DESCENDING order: warps are homogeneous, and the
+// heaviest warps are scheduled first (one warp per block, blocks issued in
+// order), which is what bounds the makespan when a batch has fewer streams
+// than the GPU has lanes.
 //
 // The per-sample body is STRAIGHT-LINE code, identical for every lane:
 //   * coefficients c[M] and the last M+1 outputs H[M+1] live in registers,
 //     statically indexed, fully unrolled over the taps; M is the smallest
-//     bucket >= the largest order among the warp's lanes (chosen per warp);
+//     bucket >= the largest order among the warp's lanes;
 //   * a lane whose order is below M keeps H[j] == base for every j > order
 //     (a masked shift), so its surplus taps see a zero difference and drop
 //     out of the dot product AND of the adaptation without any predicate;
@@ -27,6 +30,47 @@
 #include "alacgpu_kernels.h"
 
 namespace alacgpu {
+
+// ---- order sort ------------------------------------------------------------------
+// key(stream) = predictor order if K2 has work on it (1..31), else "inactive".  One block:
+// shared-memory histogram -> descending offsets -> scatter.  perm[0..n_active) = stream ids
+// (slot*2 + ch), heaviest first; perm_count[0] = n_active.
+constexpr int kSortThreads = 1024;
+
+__device__ __forceinline__ int lpc_key(const FrameDesc &d, int ch)
+{
+    const bool active = d.status == FS_OK && !(d.flags & FF_ESCAPE) && (ch == 0 || (d.flags & FF_STEREO)) &&
+                        d.order[ch] != 0 && d.n > 1;                 // order 0: output == residual (:261-267)
+    if (!active) return -1;
+    // delta mode (31) has no taps: lightest class, sorted last
+    return d.order[ch] == 31 ? 0 : d.order[ch];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *__restrict__ perm,
+               uint32_t *__restrict__ perm_count)
+{
+    __shared__ uint32_t hist[32], cursor[32];
+    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n_streams = n_frames * 2u;
+    for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
+        const int key = lpc_key(desc[s >> 1], (int)(s & 1u));
+        if (key >= 0) atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int key = 30; key >= 0; --key) { cursor[key] = acc; acc += hist[key]; }
+        cursor[31] = 0;
+        perm_count[0] = acc;
+    }
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
+        const int key = lpc_key(desc[s >> 1], (int)(s & 1u));
+        if (key >= 0) perm[atomicAdd(&cursor[key], 1u)] = s;
+    }
+}
 
 // One tap of one sample: dot-product term + sign-LMS step, branch free.  Written in PTX so
 // the update stays two predicated instructions (nvcc otherwise turns `if (E > 0)` into a
@@ -55,16 +99,16 @@ __device__ __forceinline__ void lpc_tap(int32_t &c, int32_t &E, uint32_t &acc, c
         : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "r"(negm));
 }
 
-constexpr int kK2Threads = 128;
+constexpr int kK2Threads = 32;     // one warp per block: blocks are issued heaviest first
 
 // All 32 lanes run this; `active` gates memory traffic only.
-//   p      : lane's column of the plane (sample i at p[i * 32])
-//   n      : samples of this lane's stream (0 if inactive), nmax: warp maximum
+//   row    : the lane's row of the plane (16-byte aligned), n samples (0 if inactive)
+//   nmax   : warp maximum of n
 //   ord    : 1..30 general, 31 delta mode (AlacFile.cs:268-282); inactive lanes pass 31
 template <int M>
-__device__ __noinline__ void lpc_warp(int32_t *p, const int n, const int nmax, const int rss, const int ord,
+__device__ __noinline__ void lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int ord,
                                       const int q, const int16_t *__restrict__ coef16, const bool active,
-                                      int32_t *hist /* this thread's column of a [32][blockDim] shared ring */)
+                                      int32_t *hist /* this lane's column of a [32][32] shared ring */)
 {
     const bool delta = ord == 31;
     const int ordm = delta ? 0 : ord;              // taps this lane really has
@@ -88,42 +132,58 @@ __device__ __noinline__ void lpc_warp(int32_t *p, const int n, const int nmax, c
     // r = 2^quant - 1 for a negative one (arithmetic shift of the negated magnitude, :328-329)
     const uint32_t rneg = (1u << q) - 1u;
     const int sh = (32 - rss) & 31;
+    int4 *row4 = reinterpret_cast<int4 *>(row);
+    const int nblk = (n + 3) >> 2, nblk_max = (nmax + 3) >> 2;
 
-    H[0] = active ? p[0] : 0;                                       // first sample always copies (:259-260)
+    // residual blocks are fetched two blocks (eight samples) ahead
+    int4 cur = active ? row4[0] : make_int4(0, 0, 0, 0);
+    int4 nx1 = (active && nblk > 1) ? row4[1] : make_int4(0, 0, 0, 0);
+    H[0] = cur.x;                                                   // first sample always copies (:259-260)
     hist[0] = H[0];
-    // residuals are fetched two samples ahead (HBM latency ~ one sample's worth of taps)
-    int32_t e_next = (active && n > 1) ? p[kTile] : 0;
-    int32_t e_next2 = (active && n > 2) ? p[2 * kTile] : 0;
-    for (int i = 1; i < nmax; i++) {
-        const bool live = active && i < n;
-        const int32_t e = e_next;
-        e_next = e_next2;
-        if (active && i + 2 < n) e_next2 = p[(uint32_t)(i + 2) * kTile];
-        // base of the NEXT sample, o[i - ord] (ord >= 1): from the lane's ring of its last 32
-        // outputs in shared memory ([slot][thread]: bank == lane, conflict free)
-        const int32_t nb = hist[((uint32_t)(i - ord) & 31u) * kK2Threads];
-        const bool main = !delta && i > ord;                        // warm-up covers i = 1..ord (:284-293)
-        const int32_t base = H[M];                                  // o[i-1-ord]
-        const int32_t nsg = e < 0 ? 1 : -1;                         // -sign(err)
-        const int32_t sgbase = e < 0 ? (int32_t)(0u - (uint32_t)base) : base;
-        int32_t E = main ? (e < 0 ? (int32_t)(0u - (uint32_t)e) : e) : 0;   // sign(err) * err
-        uint32_t r = e < 0 ? rneg : 0u;
-        uint32_t acc = 0;
+    for (int b = 0; b < nblk_max; b++) {
+        const int4 nx2 = (active && b + 2 < nblk) ? row4[b + 2] : make_int4(0, 0, 0, 0);
+        // The four samples of a block run through ONE copy of the tap code (the body is ~10 M
+        // instructions; unrolling it four times would overflow the instruction cache), so the
+        // block's residuals / outputs are moved with selects instead of static indices.
+        int32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+#pragma unroll 1
+        for (int u = 0; u < 4; u++) {
+            const int i = b * 4 + u;
+            const int32_t e = u == 0 ? cur.x : (u == 1 ? cur.y : (u == 2 ? cur.z : cur.w));
+            int32_t o;
+            if (i == 0) {
+                o = H[0];
+            } else {
+                // base of the NEXT sample, o[i - ord] (ord >= 1): from the lane's ring of its last 32
+                // outputs in shared memory ([slot][lane]: bank == lane, conflict free)
+                const int32_t nb = hist[((uint32_t)(i - ord) & 31u) * 32];
+                const bool main = !delta && i > ord;                        // warm-up covers i = 1..ord (:284-293)
+                const int32_t base = H[M];                                  // o[i-1-ord]
+                const int32_t nsg = e < 0 ? 1 : -1;                         // -sign(err)
+                const int32_t sgbase = e < 0 ? (int32_t)(0u - (uint32_t)base) : base;
+                int32_t E = main ? (e < 0 ? (int32_t)(0u - (uint32_t)e) : e) : 0;   // sign(err) * err
+                const uint32_t r = e < 0 ? rneg : 0u;
+                uint32_t acc = 0;
 #pragma unroll
-        for (int pp = M - 1; pp >= 0; --pp)
-            lpc_tap(c[pp], E, acc, H[pp], nsg, sgbase, r, (uint32_t)q, negm[pp]);
-        const int32_t sum = (int32_t)(acc * (uint32_t)nsg);         // sum of (buf[b+order-j]-buf[b])*coef[j]
-        int32_t v = (int32_t)((uint32_t)rnd + (uint32_t)sum) >> q;  // :306-307
-        v = (int32_t)((uint32_t)v + (uint32_t)base + (uint32_t)e);  // :308
-        const int32_t w = (int32_t)((uint32_t)H[0] + (uint32_t)e);  // warm-up / delta (:279, :288)
-        const int32_t x = main ? v : w;
-        const int32_t o = (int32_t)((uint32_t)x << sh) >> sh;       // :309-310
-        if (live) p[(uint32_t)i * kTile] = o;
-        hist[((uint32_t)i & 31u) * kK2Threads] = o;
-        // masked shift: true history up to the lane's order, the new base beyond it
+                for (int pp = M - 1; pp >= 0; --pp)
+                    lpc_tap(c[pp], E, acc, H[pp], nsg, sgbase, r, (uint32_t)q, negm[pp]);
+                const int32_t sum = (int32_t)(acc * (uint32_t)nsg);         // sum of (buf[b+order-j]-buf[b])*coef[j]
+                int32_t v = (int32_t)((uint32_t)rnd + (uint32_t)sum) >> q;  // :306-307
+                v = (int32_t)((uint32_t)v + (uint32_t)base + (uint32_t)e);  // :308
+                const int32_t w = (int32_t)((uint32_t)H[0] + (uint32_t)e);  // warm-up / delta (:279, :288)
+                const int32_t x = main ? v : w;
+                o = (int32_t)((uint32_t)x << sh) >> sh;                     // :309-310
+                hist[((uint32_t)i & 31u) * 32] = o;
+                // masked shift: true history up to the lane's order, the new base beyond it
 #pragma unroll
-        for (int j = M; j > 0; --j) H[j] = (int32_t)(((uint32_t)nb & msk[j]) | ((uint32_t)H[j - 1] & ~msk[j]));
-        H[0] = o;
+                for (int j = M; j > 0; --j) H[j] = (int32_t)(((uint32_t)nb & msk[j]) | ((uint32_t)H[j - 1] & ~msk[j]));
+                H[0] = o;
+            }
+            o0 = u == 0 ? o : o0; o1 = u == 1 ? o : o1; o2 = u == 2 ? o : o2; o3 = u == 3 ? o : o3;
+        }
+        if (active && b < nblk) row4[b] = make_int4(o0, o1, o2, o3);
+        cur = nx1;
+        nx1 = nx2;
     }
 }
 
@@ -132,46 +192,53 @@ k2_lpc(const ChunkArgs a)
 {
     __shared__ int32_t hist_smem[32 * kK2Threads];
     const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp = (tile, channel)
-    const uint32_t tile = gw >> 1;
-    const int ch = (int)(gw & 1);
-    const uint32_t slot = tile * kTile + (uint32_t)lane;
-    bool active = slot < a.n;
+    const uint32_t n_active = a.perm_count[0];
+    const uint32_t idx = blockIdx.x * 32u + (uint32_t)lane;
+    if (blockIdx.x * 32u >= n_active) return;
+    const bool active = idx < n_active;
     int n = 0, rss = 32, ord = 31, q = 0;
     const int16_t *coef16 = nullptr;
+    int32_t *row = nullptr;
     if (active) {
-        const uint64_t f = a.f0 + slot;
+        const uint32_t sid = a.perm[idx];
+        const uint64_t f = a.f0 + (sid >> 1);
+        const int ch = (int)(sid & 1u);
         const FrameDesc d = a.desc[f];
-        active = d.status == FS_OK && !(d.flags & FF_ESCAPE) && (ch == 0 || (d.flags & FF_STEREO)) &&
-                 d.order[ch] != 0 && d.n > 1;            // order 0: output == residual (:261-267)
-        if (active) {
-            n = d.n; rss = d.rss; ord = d.order[ch]; q = d.quant[ch];
-            coef16 = a.coefs[f].c[ch];
-        }
+        n = d.n; rss = d.rss; ord = d.order[ch]; q = d.quant[ch];
+        coef16 = a.coefs[f].c[ch];
+        row = a.planes + (uint64_t)sid * a.ns;
     }
-    if (!active) { n = 0; ord = 31; }
     // taps needed by this warp: delta mode (31) needs none
     const int need = active ? (ord == 31 ? 1 : ord) : 0;
     const int maxo = __reduce_max_sync(0xffffffffu, need);
-    if (maxo == 0) return;
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    int32_t *p = a.planes + ((uint64_t)tile * 2u + (uint32_t)ch) * a.ns * kTile + lane;
-    if (maxo <= 4) lpc_warp<4>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
-    else if (maxo <= 8) lpc_warp<8>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
-    else if (maxo <= 12) lpc_warp<12>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
-    else if (maxo <= 16) lpc_warp<16>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
-    else if (maxo <= 20) lpc_warp<20>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
-    else if (maxo <= 24) lpc_warp<24>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
-    else lpc_warp<30>(p, n, nmax, rss, ord, q, coef16, active, hist_smem + threadIdx.x);
+    int32_t *hist = hist_smem + lane;
+    if (maxo <= 2) lpc_warp<2>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 4) lpc_warp<4>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 6) lpc_warp<6>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 8) lpc_warp<8>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 10) lpc_warp<10>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 12) lpc_warp<12>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 14) lpc_warp<14>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 16) lpc_warp<16>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 18) lpc_warp<18>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 20) lpc_warp<20>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 22) lpc_warp<22>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 24) lpc_warp<24>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 26) lpc_warp<26>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else if (maxo <= 28) lpc_warp<28>(row, n, nmax, rss, ord, q, coef16, active, hist);
+    else lpc_warp<30>(row, n, nmax, rss, ord, q, coef16, active, hist);
 }
 
 cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    const uint32_t tiles = (a.n + kTile - 1) / kTile;
-    const uint32_t warps = tiles * 2;
-    k2_lpc<<<(warps + 3) / 4, kK2Threads, 0, st>>>(a);
-    if (launches) *launches += 1;
+    k0s_order_sort<<<1, kSortThreads, 0, st>>>(a.desc + a.f0, a.n, a.perm, a.perm_count);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint32_t warps = (a.n * 2u + 31u) / 32u;       // upper bound; warps past n_active exit at once
+    k2_lpc<<<warps, kK2Threads, 0, st>>>(a);
+    if (launches) *launches += 2;
     return cudaGetLastError();
 }
 

@@ -7,162 +7,191 @@
 // the byte stream AlacContext.Read hands out: interleaved, little-endian,
 // left first.
 //
-// HBM-bound stage.  A warp owns a 32-frame x 32-sample block of a tile:
-//   phase 1 (lane = frame)  : 128-byte coalesced plane rows -> un-mix with the
-//                             lane's own mixShift/mixWeight -> padded smem tile;
-//   phase 2 (lane = sample) : per frame, 32 consecutive samples -> one
-//                             contiguous run of the frame's PCM (128 B for
-//                             16-bit stereo, 192 B for 24-bit stereo).
-// Wasted bytes and uncompressed (escape) frames are read straight from the
-// bitstream in phase 2, where consecutive lanes read consecutive bit fields.
+// HBM-bound streaming stage.  One thread owns EIGHT consecutive sample-frames
+// of one frame: two 16-byte loads per channel from the stream-major planes,
+// un-mix with the frame's mixShift/mixWeight, and 16 / 24 / 32 / 48 bytes of
+// PCM written with 16-byte stores (consecutive threads write consecutive
+// bytes).  Wasted bytes and uncompressed (escape) frames come straight from
+// the bitstream: the thread loads the aligned 32-bit words that cover its run
+// of bit fields, shifts the run to a word boundary with funnel shifts, and
+// extracts the fields at compile-time positions.
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
 
 namespace alacgpu {
 
-constexpr int kK3Warps = 4;
+constexpr int kK3Threads = 128;
+constexpr int kK3PerThread = 8;                              // sample-frames per thread
+constexpr int kK3PerBlock = kK3Threads * kK3PerThread;       // 1024 sample-frames per block
 
-struct K3Smem {
-    int32_t tl[kK3Warps][32][33];
-    int32_t tr[kK3Warps][32][33];
-    uint32_t stage[kK3Warps][52];    // 192 B row + slack for the unaligned window
-};
-
-__global__ void __launch_bounds__(kK3Warps * 32)
-k3_stereo_pack(const ChunkArgs a, const uint32_t blocks_per_tile)
+// A run of NF big-endian bit fields of W bits each starting at absolute arena bit `pos`.
+// out[v] = field v (zero-extended).  NF * W is a multiple of 32.
+template <int NF, int W>
+__device__ __forceinline__ void read_fields(const uint32_t *__restrict__ arena32, uint64_t pos, uint32_t (&out)[NF])
 {
-    __shared__ K3Smem sm;
-    const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
-    const uint32_t unit = blockIdx.x * kK3Warps + (uint32_t)w;
-    const uint32_t tile = unit / blocks_per_tile;
-    const uint32_t i0 = (unit % blocks_per_tile) * 32u;
-    const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
-    if (tile >= n_tiles) return;
-
-    // ---- lane = frame: this lane's frame parameters -----------------------
-    const uint32_t slot = tile * kTile + (uint32_t)lane;
-    const bool have = slot < a.n;
-    FrameDesc d = {};
-    uint32_t n_eff = 0;        // sample-frames of PCM this frame emits
-    int ss = 16, nch = 2;
-    uint64_t out = 0, frame_bit = 0;
-    if (have) {
-        const uint64_t f = a.f0 + slot;
-        d = a.desc[f];
-        const FrameRef ref = a.refs[f];
-        const TrackCfg cfg = a.cfgs[ref.track];
-        ss = cfg.sample_size;
-        nch = cfg.num_channels;
-        n_eff = d.out_len / (uint32_t)((ss >> 3) * nch);
-        out = a.frame_off[f] - a.pcm_base;
-        frame_bit = ref.off * 8ull;
+    constexpr int NW = NF * W / 32;
+    const uint64_t w0 = pos >> 5;
+    const int off = (int)(pos & 31);
+    uint32_t raw[NW + 1];
+#pragma unroll
+    for (int j = 0; j <= NW; j++) raw[j] = bswap32(__ldg(arena32 + w0 + j));
+    uint32_t al[NW + 1];
+#pragma unroll
+    for (int j = 0; j < NW; j++) al[j] = __funnelshift_l(raw[j + 1], raw[j], off);
+    al[NW] = 0;
+#pragma unroll
+    for (int v = 0; v < NF; v++) {
+        const int bit = v * W, j = bit >> 5, o = bit & 31;
+        const uint32_t win = o ? __funnelshift_l(al[j + 1], al[j], o) : al[j];   // o + W may cross a word
+        out[v] = win >> (32 - W);
     }
-    // anything to do for this 32-sample block?
-    if (!__any_sync(0xffffffffu, have && i0 < n_eff)) return;
+}
 
-    const bool ok = have && d.status == FS_OK;
+// 8 sample-frames x `ech` channels of W-bit fields, interleaved A,B per sample (AlacFile.cs:634-641,
+// :665-696) -> fa[8], fb[8]
+template <int W>
+__device__ __forceinline__ void read_pairs(const uint32_t *__restrict__ arena32, uint64_t pos, bool two,
+                                           uint32_t (&fa)[8], uint32_t (&fb)[8])
+{
+    if (two) {
+        uint32_t f[16];
+        read_fields<16, W>(arena32, pos, f);
+#pragma unroll
+        for (int s = 0; s < 8; s++) { fa[s] = f[2 * s]; fb[s] = f[2 * s + 1]; }
+    } else {
+        read_fields<8, W>(arena32, pos, fa);
+#pragma unroll
+        for (int s = 0; s < 8; s++) fb[s] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kK3Threads)
+k3_stereo_pack(const ChunkArgs a)
+{
+    const uint32_t slot = blockIdx.y;
+    const uint64_t f = a.f0 + slot;
+    const FrameDesc d = a.desc[f];
+    const FrameRef ref = a.refs[f];
+    const TrackCfg cfg = a.cfgs[ref.track];
+    const int ss = cfg.sample_size;
+    const bool two_ch = cfg.num_channels == 2;
+    const bool is24 = ss == 24;
+    const uint32_t bpf = (uint32_t)(ss >> 3) * (uint32_t)cfg.num_channels;   // bytes per sample-frame
+    const uint32_t n_eff = d.out_len / bpf;                  // sample-frames of PCM this frame emits
+    const uint32_t i0 = (blockIdx.x * kK3Threads + threadIdx.x) * kK3PerThread;
+    if (i0 >= n_eff) return;
+    const uint32_t cnt = min((uint32_t)kK3PerThread, n_eff - i0);
+
+    const bool ok = d.status == FS_OK;
     const bool stereo = ok && (d.flags & FF_STEREO);
-    const bool from_planes = ok && !(d.flags & FF_ESCAPE);
-
-    // ---- phase 1: plane rows -> un-mixed L/R in the smem tile --------------
-    {
-        const int32_t *pa = a.planes + ((uint64_t)tile * 2u) * a.ns * kTile + lane;
-        const int32_t *pb = pa + (uint64_t)a.ns * kTile;
-        const int mw = d.mix_weight, ms = d.mix_shift & 31;
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
-            const uint32_t i = i0 + (uint32_t)r;
-            int32_t L = 0, R = 0;
-            if (from_planes && i < n_eff) {
-                const int32_t A = pa[(uint64_t)i * kTile];
-                if (stereo) {
-                    const int32_t B = pb[(uint64_t)i * kTile];
-                    if (mw != 0) {                                   // AlacFile.cs:342-355, :373-380
-                        R = (int32_t)((uint32_t)A - (uint32_t)((int32_t)((uint32_t)B * (uint32_t)mw) >> ms));
-                        L = (int32_t)((uint32_t)R + (uint32_t)B);
-                    } else { L = A; R = B; }                         // :359-366, :401-404
-                } else {
-                    L = A;                                           // :533-540 (second channel = 0)
-                }
-            }
-            sm.tl[w][r][lane] = L;
-            sm.tr[w][r][lane] = R;
-        }
-    }
-    __syncwarp();
-
-    // ---- phase 2: lane = sample; loop over the tile's frames ----------------
+    const bool escape = ok && (d.flags & FF_ESCAPE);
     const uint32_t *arena32 = reinterpret_cast<const uint32_t *>(a.arena);
-    // pack the per-frame scalars once so each frame costs a handful of shuffles
-    const uint32_t meta = (uint32_t)d.flags | ((uint32_t)d.ub << 8) | ((uint32_t)(ok ? 1 : 0) << 16) |
-                          ((uint32_t)(ss == 24 ? 1 : 0) << 17) | ((uint32_t)(nch == 2 ? 1 : 0) << 18);
-    for (int fr = 0; fr < 32; fr++) {
-        const uint32_t f_n = __shfl_sync(0xffffffffu, n_eff, fr);
-        if (i0 >= f_n) continue;                                     // warp-uniform
-        const uint32_t f_meta = __shfl_sync(0xffffffffu, meta, fr);
-        const uint64_t f_out = __shfl_sync(0xffffffffu, out, fr);
-        const uint64_t f_bit = __shfl_sync(0xffffffffu, frame_bit, fr);
-        const uint32_t f_data = __shfl_sync(0xffffffffu, d.data_bit, fr);
-        const uint32_t f_shift = __shfl_sync(0xffffffffu, d.shift_bit, fr);
-        const bool f_ok = (f_meta >> 16) & 1u;
-        const bool f_24 = (f_meta >> 17) & 1u;
-        const bool f_2ch = (f_meta >> 18) & 1u;
-        const bool f_stereo = f_meta & FF_STEREO;
-        const bool f_escape = f_meta & FF_ESCAPE;
-        const int f_ub = (int)((f_meta >> 8) & 0xffu);
-        const int f_ss = f_24 ? 24 : 16;
-        const int ech = f_stereo ? 2 : 1;
+    const uint64_t frame_bit = ref.off * 8ull;
+    const int ech = stereo ? 2 : 1;
 
-        const uint32_t i = i0 + (uint32_t)lane;
-        const uint32_t cnt = min(32u, f_n - i0);                     // samples of this frame in the block
-        const bool live = (uint32_t)lane < cnt;
-        int32_t L = sm.tl[w][lane][fr];
-        int32_t R = sm.tr[w][lane][fr];
-        if (live && f_ok && f_escape) {                              // AlacFile.cs:498-524, :663-696
-            const uint64_t pos = f_bit + f_data + (uint64_t)i * (uint32_t)(ech * f_ss);
-            L = sext((int32_t)arena_bits(arena32, pos, f_ss), f_ss);
-            R = f_stereo ? sext((int32_t)arena_bits(arena32, pos + (uint32_t)f_ss, f_ss), f_ss) : 0;
-        }
-        if (live && f_ok && f_24 && f_ub != 0) {                     // :381-389, :405-413, :549-554
-            const int sh = f_ub * 8;
-            const uint32_t mask = ~(0xFFFFFFFFu << sh);
-            const uint64_t pos = f_bit + f_shift + (uint64_t)i * (uint32_t)(ech * sh);
-            L = (int32_t)(((uint32_t)L << sh) | (arena_bits(arena32, pos, sh) & mask));
-            if (f_stereo) R = (int32_t)(((uint32_t)R << sh) | (arena_bits(arena32, pos + (uint32_t)sh, sh) & mask));
-        }
-        uint8_t *dst = a.pcm + f_out;
-        if (!f_24) {
-            if (f_2ch) {                                             // AlacContext.cs:231-242: low 16 bits, LE
-                if (live)
-                    reinterpret_cast<uint32_t *>(dst)[i] = ((uint32_t)L & 0xffffu) | ((uint32_t)R << 16);
-            } else {
-                if (live) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)L;
+    int32_t L[8], R[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) { L[s] = 0; R[s] = 0; }
+
+    if (ok && !escape) {
+        // predicted samples: rows are padded to a multiple of 8, so the loads never leave the row
+        const int4 *ra = reinterpret_cast<const int4 *>(a.planes + ((uint64_t)slot * 2u) * a.ns + i0);
+        const int4 a0 = ra[0], a1 = ra[1];
+        int32_t A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (stereo) {
+            const int4 *rb = reinterpret_cast<const int4 *>(a.planes + ((uint64_t)slot * 2u + 1u) * a.ns + i0);
+            const int4 b0 = rb[0], b1 = rb[1];
+            int32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const int mw = d.mix_weight, ms = d.mix_shift & 31;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                if (mw != 0) {                                       // AlacFile.cs:342-355, :373-380
+                    R[s] = (int32_t)((uint32_t)A[s] - (uint32_t)((int32_t)((uint32_t)B[s] * (uint32_t)mw) >> ms));
+                    L[s] = (int32_t)((uint32_t)R[s] + (uint32_t)B[s]);
+                } else { L[s] = A[s]; R[s] = B[s]; }                 // :359-366, :401-404
             }
         } else {
-            // 24-bit: bytes L0 L1 L2 [R0 R1 R2] (AlacFile.cs:390-395, :555-557) staged per row,
-            // then written as aligned 32-bit words with byte-granular edges.
-            const uint32_t bpf = f_2ch ? 6u : 3u;
-            uint8_t *stg = reinterpret_cast<uint8_t *>(sm.stage[w]);
-            __syncwarp();
-            if (live) {
-                uint8_t *q = stg + (uint32_t)lane * bpf;
-                q[0] = (uint8_t)L; q[1] = (uint8_t)((uint32_t)L >> 8); q[2] = (uint8_t)((uint32_t)L >> 16);
-                if (f_2ch) { q[3] = (uint8_t)R; q[4] = (uint8_t)((uint32_t)R >> 8); q[5] = (uint8_t)((uint32_t)R >> 16); }
+#pragma unroll
+            for (int s = 0; s < 8; s++) L[s] = A[s];                 // :533-540 (second channel = 0)
+        }
+        if (is24 && d.ub != 0) {                                     // :381-389, :405-413, :549-554
+            const int sh = d.ub * 8;
+            const uint32_t mask = ~(0xFFFFFFFFu << sh);
+            const uint64_t pos = frame_bit + d.shift_bit + (uint64_t)i0 * (uint32_t)(ech * sh);
+            uint32_t fa[8], fb[8];
+            if (d.ub == 1) read_pairs<8>(arena32, pos, stereo, fa, fb);
+            else if (d.ub == 2) read_pairs<16>(arena32, pos, stereo, fa, fb);
+            else read_pairs<24>(arena32, pos, stereo, fa, fb);
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                L[s] = (int32_t)(((uint32_t)L[s] << sh) | (fa[s] & mask));
+                if (stereo) R[s] = (int32_t)(((uint32_t)R[s] << sh) | (fb[s] & mask));
             }
-            __syncwarp();
-            uint8_t *row = dst + (uint64_t)i0 * bpf;
-            const uint32_t len = cnt * bpf;
-            const uint32_t head = min(len, (uint32_t)((0u - (uint32_t)(uintptr_t)row) & 3u));
-            const uint32_t nwords = (len - head) >> 2;
-            const uint32_t tail = len - head - (nwords << 2);
-            if ((uint32_t)lane < head) row[lane] = stg[lane];
-            uint32_t *row32 = reinterpret_cast<uint32_t *>(row + head);
-            for (uint32_t k = (uint32_t)lane; k < nwords; k += 32u) {
-                const uint32_t lo = sm.stage[w][k], hi = sm.stage[w][k + 1];
-                row32[k] = __funnelshift_r(lo, hi, head * 8u);
+        }
+    } else if (escape) {                                             // AlacFile.cs:498-524, :663-696
+        const uint64_t pos = frame_bit + d.data_bit + (uint64_t)i0 * (uint32_t)(ech * ss);
+        uint32_t fa[8], fb[8];
+        if (is24) read_pairs<24>(arena32, pos, stereo, fa, fb);
+        else read_pairs<16>(arena32, pos, stereo, fa, fb);
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            L[s] = sext((int32_t)fa[s], ss);
+            R[s] = stereo ? sext((int32_t)fb[s], ss) : 0;
+        }
+    }
+
+    // ---- pack: little-endian, left first; 16-bit = low 16 bits of each int (AlacContext.cs:231-242),
+    // 24-bit = low 24 bits (AlacFile.cs:390-395, :555-557) -----------------------------------------
+    uint32_t w[12];
+    if (!is24) {
+        if (two_ch) {
+#pragma unroll
+            for (int s = 0; s < 8; s++) w[s] = ((uint32_t)L[s] & 0xffffu) | ((uint32_t)R[s] << 16);
+        } else {
+#pragma unroll
+            for (int s = 0; s < 4; s++) w[s] = ((uint32_t)L[2 * s] & 0xffffu) | ((uint32_t)L[2 * s + 1] << 16);
+        }
+    } else {
+        if (two_ch) {
+            // per pair of sample-frames: L0 R0 L1 R1 (4 x 24 bits) -> 3 words
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const uint32_t l0 = (uint32_t)L[2 * p] & 0xffffffu, r0 = (uint32_t)R[2 * p] & 0xffffffu;
+                const uint32_t l1 = (uint32_t)L[2 * p + 1] & 0xffffffu, r1 = (uint32_t)R[2 * p + 1] & 0xffffffu;
+                w[3 * p] = l0 | (r0 << 24);
+                w[3 * p + 1] = (r0 >> 8) | (l1 << 16);
+                w[3 * p + 2] = (l1 >> 16) | (r1 << 8);
             }
-            if ((uint32_t)lane < tail) row[head + (nwords << 2) + lane] = stg[head + (nwords << 2) + lane];
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const uint32_t s0 = (uint32_t)L[4 * p] & 0xffffffu, s1 = (uint32_t)L[4 * p + 1] & 0xffffffu;
+                const uint32_t s2 = (uint32_t)L[4 * p + 2] & 0xffffffu, s3 = (uint32_t)L[4 * p + 3] & 0xffffffu;
+                w[3 * p] = s0 | (s1 << 24);
+                w[3 * p + 1] = (s1 >> 8) | (s2 << 16);
+                w[3 * p + 2] = (s2 >> 16) | (s3 << 8);
+            }
+        }
+    }
+    const uint32_t nbytes = cnt * bpf;                               // 16, 24, 32 or 48 when cnt == 8
+    uint8_t *dst = a.pcm + (a.frame_off[f] - a.pcm_base) + (uint64_t)i0 * bpf;
+    if (cnt == kK3PerThread && ((uintptr_t)dst & 15u) == 0) {
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (nbytes == 24) {
+            reinterpret_cast<uint2 *>(dst)[2] = make_uint2(w[4], w[5]);
+        } else if (nbytes >= 32) {
+            d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (nbytes == 48) d4[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        }
+    } else {
+        // partial last group of a frame, or a frame that starts off a 16-byte boundary (after an
+        // odd-sized partial frame): byte stores from statically indexed registers
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+                if ((uint32_t)(j * 4 + bb) < nbytes) dst[j * 4 + bb] = (uint8_t)(w[j] >> (8 * bb));
         }
     }
 }
@@ -170,11 +199,10 @@ k3_stereo_pack(const ChunkArgs a, const uint32_t blocks_per_tile)
 cudaError_t launch_k3(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    const uint32_t tiles = (a.n + kTile - 1) / kTile;
-    const uint32_t bpt = (a.ns + 31) / 32;
-    const uint64_t units = (uint64_t)tiles * bpt;
-    const uint32_t blocks = (uint32_t)((units + kK3Warps - 1) / kK3Warps);
-    k3_stereo_pack<<<blocks, kK3Warps * 32, 0, st>>>(a, bpt);
+    const uint32_t bx = (a.max_sf + kK3PerBlock - 1) / kK3PerBlock;
+    // grid.y is limited to 65535: chunks hold at most 32768 frames
+    dim3 grid(bx ? bx : 1, a.n, 1);
+    k3_stereo_pack<<<grid, kK3Threads, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

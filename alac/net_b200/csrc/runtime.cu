@@ -87,6 +87,7 @@ struct Chunk {
 struct Slot {
     cudaStream_t st = nullptr;
     DevBuf<int32_t> planes;
+    DevBuf<uint32_t> perm;        // K2 work list (2 entries per frame) + 1 count word at the end
 };
 
 struct Device {
@@ -107,7 +108,7 @@ struct Device {
     DevBuf<uint8_t> pcm;
     uint64_t pcm_lo = 0, pcm_hi = 0;  // global byte range held by `pcm` (pcm_lo 256-aligned)
     uint64_t pcm_first = 0;           // global offset of the first byte this shard produces
-    uint32_t ns = 32;                 // plane stride (samples), multiple of 32
+    uint32_t ns = 64;                 // plane row stride (samples): multiple of 32, plus 32 so rows are not 16 KiB apart
     std::vector<FrameRef> h_refs;
     std::vector<HostCopy> track_copies;   // one per (track, device): host bytes -> arena
     std::vector<HostCopy> copies;         // the same bytes split at chunk boundaries
@@ -282,7 +283,7 @@ int32_t build_plan(alacgpu_ctx *ctx)
             used = base + (src_hi - src_lo);
         }
         d.arena_used = used;
-        d.ns = std::max<uint32_t>((ctx->max_sf + 31u) & ~31u, 32u);
+        d.ns = std::max<uint32_t>((ctx->max_sf + 31u) & ~31u, 32u) + 32u;
         // PCM byte range of the shard (contiguous in the global layout)
         if (n_local) {
             d.pcm_first = ctx->frame_off[d.f_lo];
@@ -379,7 +380,8 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ChunkArgs ca{};
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
-    ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n;
+    ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
+    ca.perm = s.perm.p; ca.perm_count = s.perm.p + 2u * (size_t)d.chunk_frames;
     CU(cudaEventRecord(get_event(d, ev), s.st));
     if (with_k0) {
         K0Args ka{};
@@ -421,7 +423,10 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         const size_t n_chunks = d.chunks.size();
         const int slots_used = (int)std::min<size_t>(kSlots, n_chunks);
         if (decode)
-            for (int s = 0; s < slots_used; s++) CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
+            for (int s = 0; s < slots_used; s++) {
+                CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
+                CU(d.slots[s].perm.reserve((size_t)cf * 2u + 4u));
+            }
         get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
         CU(cudaEventRecord(d.events[0], d.slots[0].st));
         for (int s = 1; s < slots_used; s++) CU(cudaStreamWaitEvent(d.slots[s].st, d.events[0], 0));
@@ -602,7 +607,7 @@ int32_t alacgpu_destroy(alacgpu_ctx *ctx)
         cudaDeviceSynchronize();
         d.arena.release(); d.refs.release(); d.cfgs.release(); d.desc.release(); d.coefs.release();
         d.expect_len.release(); d.frame_off.release(); d.scalars.release(); d.pcm.release();
-        for (Slot &s : d.slots) { s.planes.release(); if (s.st) cudaStreamDestroy(s.st); }
+        for (Slot &s : d.slots) { s.planes.release(); s.perm.release(); if (s.st) cudaStreamDestroy(s.st); }
         for (cudaEvent_t e : d.events) cudaEventDestroy(e);
         if (d.st_h2d) cudaStreamDestroy(d.st_h2d);
         if (d.st_d2h) cudaStreamDestroy(d.st_d2h);
