@@ -170,6 +170,7 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
     const uint32_t kmask = (1u << kmod) - 1u;                // AlacFile.cs:483,:643
     const int ech = (d.flags & FF_STEREO) ? 2 : 1;
     const int ech_max = __reduce_max_sync(0xffffffffu, n ? ech : 0);
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
 
     BitCursor br;
     br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull,
@@ -183,91 +184,90 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
         int4 *row = reinterpret_cast<int4 *>(a.planes + ((uint64_t)(work ? slot : 0u) * 2u + (uint32_t)c) * a.ns);
         const uint32_t mult = (uint32_t)((int32_t)d.rice_mod[c & 1] * (cfg.rice_history_mult / 4));   // :483
         int nc = c < ech ? n : 0;                // samples this lane decodes in this channel
-        int cnt = 0;                             // residuals produced so far (== the reference's outputCount)
-        int flushed = 0;                         // residuals already stored to the row
         int32_t h = cfg.rice_initial_history;    // :216
         uint32_t sm1 = 0xFFFFFFFFu;              // signModifier - 1
         uint32_t zcnt = 0;                       // zeros of the current run still to emit
-        bool isz = false;                        // next field belongs to a zero-run length symbol
-        bool rawp = false;                       // next field is the raw value after nine 1 bits
         int k = min(flo((uint32_t)((h >> 9) + 3)), kmod);        // :221-222
+        uint32_t m0 = (1u << k) - 1u;
 
-        for (;;) {
+        for (int i0 = 0; i0 < nmax; i0 += kFlushEvery) {
             br.top_up();
             cp_async_wait<1>();                  // everything but the group just committed
 #pragma unroll 1
-            for (int it = 0; it < kFlushEvery; it++) {
-                // ---- what this lane does in this iteration -------------------------------
-                const bool more = cnt < nc;
-                const bool zero = more && zcnt != 0;             // emit one zero of a run
-                const bool act = more && zcnt == 0;              // read one bit field
+            for (int i4 = i0; i4 < i0 + kFlushEvery; i4 += 4) {
+              int32_t out[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int i = i4 + u;
+                // ---- common case, one straight-line block: every lane evaluates the Rice symbol at
+                // its cursor; lanes inside a zero run or past their last sample commit nothing ----
+                const bool live = zcnt == 0 && i < nc;
                 const uint32_t w = br.peek();
                 const int p = flo(~w);                           // bit index of the first 0 bit
-                const bool esc = w >= 0xFF800000u;               // nine 1 bits (:198)
-                const bool rice = act && !rawp && !esc;          // a complete Rice symbol
-                const bool got = act && (rawp || !esc);          // this iteration completes a symbol
-                const bool gotm = got && !isz, gotz = got && isz;
-                const int rb = isz ? 16 : rss;                   // raw field width (:201, :236)
-                // ---- the field --------------------------------------------------------------
-                const uint32_t m0 = rawp ? 0u : (1u << k) - 1u;
                 const uint32_t e = (w >> ((p - k) & 31)) & m0;   // k bits after the terminator (:205)
-                const uint32_t em = max(e, 1u);                  // raw: m0 == 0 -> em == 1
-                const uint32_t mm = isz ? (m0 & kmask) : m0;     // :206 multiplier
-                // A + em = decoded value (+ signModifier for a sample):  Rice x*mm + max(e,1) - 1,
-                // raw field w >> (32 - rb)
-                const uint32_t x = (uint32_t)(31 - p);
-                const uint32_t smz = isz ? 0xFFFFFFFFu : sm1;
-                const uint32_t A = (rawp ? (w >> (32 - rb)) : x * mm) + smz;
-                const uint32_t dv = A + em;
-                // ---- cursor: Rice consumes x + k (+1 if e >= 2) bits (:210), raw rb, escape prefix 9
-                const uint32_t t_rice = br.off + (uint32_t)(31 + k - p);
-                const uint32_t t_else = br.off + (act ? (rawp ? (uint32_t)rb : 9u) : 0u);
-                const uint32_t t = (rice ? t_rice : t_else) + ((rice && e >= 2u) ? 1u : 0u);
-                br.seek(t);
-                // ---- history (:229): samples update it, a run length resets it (:248) -------------
-                const uint32_t mult_e = gotm ? mult : 0u;
-                const int32_t hb = gotz ? 0 : (gotm ? h - ((int32_t)((uint32_t)h * mult) >> 9) : h);
-                const int32_t hn = (int32_t)(em * mult_e + (A * mult_e + (uint32_t)hb));
-                h = (gotm && dv > 0xFFFFu) ? 0xFFFF : hn;
-                // ---- outputs ------------------------------------------------------------------------
-                const int32_t val = (int32_t)(dv >> 1) ^ -(int32_t)(dv & 1u);         // :225-226
-                const bool emit = gotm || zero;
-                if (emit) sts32(out_ring + (((uint32_t)cnt & (kOutSlots - 1)) << 7), zero ? 0 : val);
-                cnt += emit ? 1 : 0;
-                // ---- state ----------------------------------------------------------------------------
-                zcnt = gotz ? dv : zcnt - (zero ? 1u : 0u);                           // :238-245
-                sm1 = gotm ? 0xFFFFFFFFu : (gotz ? (dv > 0xFFFFu ? 0xFFFFFFFFu : 0u) : sm1);   // :227, :233, :246
-                rawp = act && !rawp && esc;
-                const bool toz = gotm && h < 128 && cnt < nc;                         // :231 (cnt is already i + 1)
-                isz = got ? toz : isz;
-                if (__builtin_expect((gotm && h < 0) || (gotz && dv != 0 && (uint32_t)cnt + dv > (uint32_t)kMaxFrameSamples), 0)) {
-                    status = h < 0 ? FS_HISTORY : FS_RUN_OVERFLOW;                    // reference: garbage k / IndexOutOfRange
-                    nc = n = 0;
+                const uint32_t em = max(e, 1u);
+                const uint32_t A = (uint32_t)(31 - p) * m0 + sm1;                     // :206, :224
+                uint32_t dv = A + em;                                                 // x*m + max(e,1) - 1 + signModifier
+                const bool ok = live && w < 0xFF800000u;         // fewer than nine 1 bits (:198)
+                // Rice consumes x + k bits, one more if e >= 2 (:210)
+                br.seek(br.off + (ok ? (uint32_t)(31 + k - p) + (e >= 2u ? 1u : 0u) : 0u));
+                const int32_t hb = h - ((int32_t)((uint32_t)h * mult) >> 9);
+                const int32_t hn = (int32_t)(em * mult + (A * mult + (uint32_t)hb));
+                h = ok ? (dv > 0xFFFFu ? 0xFFFF : hn) : h;                            // :229
+                int32_t val = (int32_t)(dv >> 1) ^ -(int32_t)(dv & 1u);               // :225-226
+                val = ok ? val : 0;
+                sm1 = ok ? 0xFFFFFFFFu : sm1;
+                zcnt -= (zcnt != 0) ? 1u : 0u;                                        // :240-243, one zero per step
+                // ---- rare per lane, but some lane of the warp needs it every few samples: the
+                // nine-ones escape (:198-202) and the zero-run symbol after a small history
+                // (:231-249).  A plain divergent branch: a warp vote in front of it costs more
+                // (vote + re-synchronisation, ~100 cycles per sample measured) than it saves. ----
+                const bool need = live && (!ok || h < 128);
+                {
+                    if (__builtin_expect(need, 0)) {
+                        if (!ok) {
+                            br.seek(br.off + 9u);
+                            dv = (br.peek() >> (32 - rss)) + (sm1 + 1u);
+                            br.seek(br.off + (uint32_t)rss);
+                            val = (int32_t)(dv >> 1) ^ -(int32_t)(dv & 1u);
+                            h = dv > 0xFFFFu ? 0xFFFF : (int32_t)(dv * mult + (uint32_t)hb);
+                            sm1 = 0xFFFFFFFFu;
+                        }
+                        if (h < 0) {
+                            status = FS_HISTORY;                                      // reference: garbage k
+                            nc = n = 0;
+                        } else if (h < 128 && i + 1 < nc) {                           // :231
+                            const int kz = (h == 0 ? 40 : 31 - flo((uint32_t)h)) + ((h + 16) >> 6) - 24;   // :234 (clz(0) == 40)
+                            const uint32_t mz = (1u << kz) - 1u;
+                            const uint32_t wz = br.peek();
+                            uint32_t block;
+                            if (wz >= 0xFF800000u) {                                  // :198-202 with 16 raw bits
+                                br.seek(br.off + 9u);
+                                block = br.peek() >> 16;
+                                br.seek(br.off + 16u);
+                            } else {
+                                const int pz = flo(~wz);
+                                const uint32_t ez = (wz >> ((pz - kz) & 31)) & mz;
+                                block = (uint32_t)(31 - pz) * (mz & kmask) + max(ez, 1u) - 1u;   // :236
+                                br.seek(br.off + (uint32_t)(31 + kz - pz) + (ez >= 2u ? 1u : 0u));
+                            }
+                            if (block > 0 && (uint32_t)i + 1u + block > (uint32_t)kMaxFrameSamples) {
+                                status = FS_RUN_OVERFLOW;                             // reference: IndexOutOfRange
+                                nc = n = 0;
+                            }
+                            zcnt = block;
+                            sm1 = block > 0xFFFFu ? 0xFFFFFFFFu : 0u;                 // :233,:246
+                            h = 0;                                                    // :248
+                        }
+                    }
                 }
-                // ---- k of the next field: :221-222, or :234 for a run length (clz(0) == 40) -------------
-                const int km = min(flo((uint32_t)((h >> 9) + 3)), kmod);
-                const int kz = (h == 0 ? 40 : 31 - flo((uint32_t)h)) + ((h + 16) >> 6) - 24;
-                k = isz ? kz : km;
+                out[u] = val;
+                k = min(flo((uint32_t)((h >> 9) + 3)), kmod);                         // :221-222
+                m0 = (1u << k) - 1u;
+              }
+              // four residuals leave the lane as one 16-byte store into its row
+              if (i4 < nc) row[i4 >> 2] = make_int4(out[0], out[1], out[2], out[3]);
             }
-            // ---- flush complete groups of four residuals (at most two are pending) -----------------
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                if (flushed + 4 <= cnt) {
-                    const uint32_t s0 = (uint32_t)flushed & (kOutSlots - 1);
-                    row[flushed >> 2] = make_int4((int32_t)lds32(out_ring + (s0 << 7)), (int32_t)lds32(out_ring + ((s0 + 1) << 7)),
-                                                  (int32_t)lds32(out_ring + ((s0 + 2) << 7)), (int32_t)lds32(out_ring + ((s0 + 3) << 7)));
-                    flushed += 4;
-                }
-            }
-            if (__all_sync(0xffffffffu, cnt >= nc)) break;
-        }
-        // tail: the last 1..3 residuals of the channel, zero padded (rows are padded to a multiple of 8)
-        if (flushed < cnt) {
-            int32_t v[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                v[j] = flushed + j < cnt ? (int32_t)lds32(out_ring + ((((uint32_t)flushed + j) & (kOutSlots - 1)) << 7)) : 0;
-            row[flushed >> 2] = make_int4(v[0], v[1], v[2], v[3]);
         }
     }
     if (work) {
