@@ -18,6 +18,7 @@ ERR_NAMES = {
     -5: "UNSUPPORTED", -6: "CAPACITY", -7: "STATE", -8: "RANGE",
 }
 FLAG_KEEP_DEVICE_PCM = 0x1
+FLAG_NO_FUSION = 0x2
 
 # every symbol include/alacgpu.h declares (tests check the export table against this)
 EXPORTS = [

@@ -13,7 +13,7 @@ HOST = os.path.join(HERE, "host")
 LIB_GPU = os.path.join(HERE, "libalacgpu.so")
 LIB_HOST = os.path.join(HERE, "libalacnet_host.so")
 
-CU_SOURCES = ["k0_index.cu", "k1_entropy.cu", "k2_lpc.cu", "k3_stereo.cu", "runtime.cu"]
+CU_SOURCES = ["k0_index.cu", "k12_decode.cu", "k3_stereo.cu", "runtime.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--shared", "-cudart", "static",

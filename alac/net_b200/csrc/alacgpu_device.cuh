@@ -31,7 +31,7 @@ constexpr int kMaxFramePcmBytes = 65536;  // AlacContext.cs:218
 // Frame status codes == ALACGPU_FRAME_* (include/alacgpu.h).
 enum : uint8_t {
     FS_OK = 0, FS_BAD_TAG = 1, FS_PRED_TYPE = 2, FS_TOO_MANY = 3, FS_OVERRUN = 4,
-    FS_BAD_RSS = 5, FS_HISTORY = 6, FS_RUN_OVERFLOW = 7, FS_ORDER0_LONG = 8
+    FS_BAD_RSS = 5, FS_HISTORY = 6, FS_RUN_OVERFLOW = 7, FS_ORDER0_LONG = 8, FS_INTERNAL = 9
 };
 
 enum : uint8_t { FF_STEREO = 1, FF_ESCAPE = 2 };

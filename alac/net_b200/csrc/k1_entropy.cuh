@@ -44,6 +44,7 @@
 // "some symbol ended past the frame's last bit" is decided once from the
 // final cursor (OVERRUN outranks a HISTORY / RUN_OVERFLOW fault).  The arena
 // carries enough tail padding for a lane that runs past its frame.
+#pragma once
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
 
@@ -51,7 +52,6 @@ namespace alacgpu {
 
 constexpr int kRingChunks = 16;              // 256 B of bitstream per lane
 constexpr int kRingBytes = kRingChunks * 16;
-constexpr int kOutSlots = 16;                // residual ring: 16 slots x 32 lanes x 4 B per warp
 constexpr int kFlushEvery = 8;               // iterations between flush / top-up points
 constexpr int kK1Threads = 128;
 
@@ -147,14 +147,24 @@ struct BitCursor {
     __device__ __forceinline__ uint32_t consumed() const { return words * 32u + off - off0; }
 };
 
-__global__ void __launch_bounds__(kK1Threads)
-k1_entropy(const ChunkArgs a, const int lanes_log2)
+// Progress hand-off to the LPC warps of the fused kernel (k12_decode.cu): a lane publishes how
+// many residuals of its stream are in the plane (every 32 samples: fence, then a relaxed
+// store the consumer reads with ld.acquire) and 0xFFFFFFFF when the channel is complete.
+__device__ __forceinline__ void publish(uint32_t *p, uint32_t v)
 {
-    __shared__ __align__(256) uint8_t ring_smem[kRingBytes * kK1Threads];
-    __shared__ int32_t out_smem[(kK1Threads / 32) * kOutSlots * 32];
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr uint32_t kStreamDone = 0xFFFFFFFFu;
+
+// One block of 128 threads = 4 entropy warps.  `block` is the index among the entropy blocks;
+// ring_smem: kRingBytes * kK1Threads bytes, 256-byte aligned.
+template <bool kPublish>
+__device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lanes_log2, const uint32_t block,
+                                              uint8_t *ring_smem)
+{
     const int lane = threadIdx.x & 31;
     const int S = 1 << lanes_log2;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t gw = (block * kK1Threads + threadIdx.x) >> 5;
     const uint32_t slot = gw * (uint32_t)S + (uint32_t)lane;
     // Every lane stays in the loops (their exits are warp votes); a lane without work runs
     // with n == 0 and commits nothing.
@@ -175,9 +185,6 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
     BitCursor br;
     br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull,
             (uint32_t)__cvta_generic_to_shared(ring_smem) + threadIdx.x * (uint32_t)kRingBytes);
-    // residual ring: slot s of this lane at out_ring + s * 128 (bank == lane)
-    const uint32_t out_ring = (uint32_t)__cvta_generic_to_shared(out_smem) +
-                              (uint32_t)(threadIdx.x >> 5) * (kOutSlots * 128u) + (uint32_t)lane * 4u;
 
     uint8_t status = FS_OK;
     for (int c = 0; c < ech_max; c++) {
@@ -189,6 +196,7 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
         uint32_t zcnt = 0;                       // zeros of the current run still to emit
         int k = min(flo((uint32_t)((h >> 9) + 3)), kmod);        // :221-222
         uint32_t m0 = (1u << k) - 1u;
+        uint32_t *prog = a.progress + ((uint64_t)(work ? slot : 0u) * 2u + (uint32_t)c);
 
         for (int i0 = 0; i0 < nmax; i0 += kFlushEvery) {
             br.top_up();
@@ -267,7 +275,15 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
               }
               // four residuals leave the lane as one 16-byte store into its row
               if (i4 < nc) row[i4 >> 2] = make_int4(out[0], out[1], out[2], out[3]);
+              if (kPublish && ((i4 + 4) & 31) == 0) {        // warp-uniform
+                  __threadfence();
+                  if (i4 < nc) publish(prog, (uint32_t)i4 + 4u);
+              }
             }
+        }
+        if (kPublish) {
+            __threadfence();
+            if (work && c < ech) publish(prog, kStreamDone);
         }
     }
     if (work) {
@@ -275,21 +291,6 @@ k1_entropy(const ChunkArgs a, const int lanes_log2)
         if (d.data_bit + br.consumed() > ref.len * 8u) status = FS_OVERRUN;
         if (status != FS_OK) a.desc[f].status = status;
     }
-}
-
-cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches)
-{
-    if (a.n == 0) return cudaSuccess;
-    int lg = 5;
-    if (lanes_per_warp == 16) lg = 4;
-    else if (lanes_per_warp == 8) lg = 3;
-    else if (lanes_per_warp == 4) lg = 2;
-    const uint32_t S = 1u << lg;
-    const uint32_t warps = (a.n + S - 1) / S;
-    const uint32_t blocks = (warps + 3) / 4;
-    k1_entropy<<<blocks, kK1Threads, 0, st>>>(a, lg);
-    if (launches) *launches += 1;
-    return cudaGetLastError();
 }
 
 }  // namespace alacgpu

@@ -26,6 +26,7 @@
 //     sign-normalised error E = sign(err) * err;
 //   * warm-up samples, delta mode (order 31) and zero residuals run the same
 //     code with E = 0 and a select on the output.
+#pragma once
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
 
@@ -99,16 +100,47 @@ __device__ __forceinline__ void lpc_tap(int32_t &c, int32_t &E, uint32_t &acc, c
         : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "r"(negm));
 }
 
-constexpr int kK2Threads = 32;     // one warp per block: blocks are issued heaviest first
+constexpr int kK2Threads = 128;    // four LPC warps per block; blocks are issued heaviest first
 
 // All 32 lanes run this; `active` gates memory traffic only.
 //   row    : the lane's row of the plane (16-byte aligned), n samples (0 if inactive)
 //   nmax   : warp maximum of n
 //   ord    : 1..30 general, 31 delta mode (AlacFile.cs:268-282); inactive lanes pass 31
-template <int M>
-__device__ __noinline__ void lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int ord,
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Fused kernel only: block until the entropy lane that produces this stream has published at
+// least `need` residuals.  Bounded: a producer that never shows up (a bug, not a data
+// condition) flags the lane instead of hanging the GPU.
+constexpr uint32_t kSpinLimit = 1u << 18;
+// Warp-uniform on purpose: every lane polls its own stream's word, but the loop exit is a
+// warp vote, so the lanes leave together (a per-lane spin loop lets the warp fall apart and
+// run the tap code lane by lane afterwards).
+__device__ __forceinline__ void wait_avail(const uint32_t *prog, const uint32_t need, uint32_t &avail,
+                                           const bool active, bool &stalled)
+{
+    for (uint32_t spins = 0;; ++spins) {
+        if (active && avail < need) avail = ld_acquire(prog);
+        const bool ok = !active || avail >= need;
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (spins >= kSpinLimit) {
+            stalled = stalled || !ok;
+            avail = 0xFFFFFFFFu;
+            break;
+        }
+        __nanosleep(256);
+    }
+}
+
+template <int M, bool kPoll>
+__device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int ord,
                                       const int q, const int16_t *__restrict__ coef16, const bool active,
-                                      int32_t *hist /* this lane's column of a [32][32] shared ring */)
+                                      int32_t *hist /* this lane's column of a [32][32] shared ring */,
+                                      const uint32_t *prog)
 {
     const bool delta = ord == 31;
     const int ordm = delta ? 0 : ord;              // taps this lane really has
@@ -136,12 +168,17 @@ __device__ __noinline__ void lpc_warp(int32_t *row, const int n, const int nmax,
     const int nblk = (n + 3) >> 2, nblk_max = (nmax + 3) >> 2;
 
     // residual blocks are fetched two blocks (eight samples) ahead
-    int4 cur = active ? row4[0] : make_int4(0, 0, 0, 0);
-    int4 nx1 = (active && nblk > 1) ? row4[1] : make_int4(0, 0, 0, 0);
+    uint32_t avail = kPoll ? 0u : 0xFFFFFFFFu;
+    bool stalled = false;
+    if (kPoll) wait_avail(prog, (uint32_t)min(nblk, 10) * 4u, avail, active, stalled);
+    int4 cur = active ? __ldcg(row4) : make_int4(0, 0, 0, 0);
+    int4 nx1 = (active && nblk > 1) ? __ldcg(row4 + 1) : make_int4(0, 0, 0, 0);
     H[0] = cur.x;                                                   // first sample always copies (:259-260)
     hist[0] = H[0];
     for (int b = 0; b < nblk_max; b++) {
-        const int4 nx2 = (active && b + 2 < nblk) ? row4[b + 2] : make_int4(0, 0, 0, 0);
+        // every 8 blocks: make sure the 32 residuals after the ones already granted are there
+        if (kPoll && (b & 7) == 7) wait_avail(prog, (uint32_t)min(nblk, b + 11) * 4u, avail, active, stalled);
+        const int4 nx2 = (active && b + 2 < nblk) ? __ldcg(row4 + b + 2) : make_int4(0, 0, 0, 0);
         // The four samples of a block run through ONE copy of the tap code (the body is ~10 M
         // instructions; unrolling it four times would overflow the instruction cache), so the
         // block's residuals / outputs are moved with selects instead of static indices.
@@ -185,61 +222,57 @@ __device__ __noinline__ void lpc_warp(int32_t *row, const int n, const int nmax,
         cur = nx1;
         nx1 = nx2;
     }
+    return stalled;
 }
 
-__global__ void __launch_bounds__(kK2Threads)
-k2_lpc(const ChunkArgs a)
+// One LPC warp: streams perm[warp * 32 + lane].  hist: this warp's [32][32] int32 ring.
+template <bool kPoll>
+__device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp, int32_t *hist_warp)
 {
-    __shared__ int32_t hist_smem[32 * kK2Threads];
     const int lane = threadIdx.x & 31;
     const uint32_t n_active = a.perm_count[0];
-    const uint32_t idx = blockIdx.x * 32u + (uint32_t)lane;
-    if (blockIdx.x * 32u >= n_active) return;
+    const uint32_t idx = warp * 32u + (uint32_t)lane;
+    if (warp * 32u >= n_active) return;
     const bool active = idx < n_active;
     int n = 0, rss = 32, ord = 31, q = 0;
     const int16_t *coef16 = nullptr;
     int32_t *row = nullptr;
+    const uint32_t *prog = nullptr;
+    uint64_t f = 0;
     if (active) {
         const uint32_t sid = a.perm[idx];
-        const uint64_t f = a.f0 + (sid >> 1);
+        f = a.f0 + (sid >> 1);
         const int ch = (int)(sid & 1u);
         const FrameDesc d = a.desc[f];
         n = d.n; rss = d.rss; ord = d.order[ch]; q = d.quant[ch];
         coef16 = a.coefs[f].c[ch];
         row = a.planes + (uint64_t)sid * a.ns;
+        prog = a.progress + sid;
     }
     // taps needed by this warp: delta mode (31) needs none
     const int need = active ? (ord == 31 ? 1 : ord) : 0;
     const int maxo = __reduce_max_sync(0xffffffffu, need);
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    int32_t *hist = hist_smem + lane;
-    if (maxo <= 2) lpc_warp<2>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 4) lpc_warp<4>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 6) lpc_warp<6>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 8) lpc_warp<8>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 10) lpc_warp<10>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 12) lpc_warp<12>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 14) lpc_warp<14>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 16) lpc_warp<16>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 18) lpc_warp<18>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 20) lpc_warp<20>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 22) lpc_warp<22>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 24) lpc_warp<24>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 26) lpc_warp<26>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else if (maxo <= 28) lpc_warp<28>(row, n, nmax, rss, ord, q, coef16, active, hist);
-    else lpc_warp<30>(row, n, nmax, rss, ord, q, coef16, active, hist);
-}
-
-cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
-{
-    if (a.n == 0) return cudaSuccess;
-    k0s_order_sort<<<1, kSortThreads, 0, st>>>(a.desc + a.f0, a.n, a.perm, a.perm_count);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const uint32_t warps = (a.n * 2u + 31u) / 32u;       // upper bound; warps past n_active exit at once
-    k2_lpc<<<warps, kK2Threads, 0, st>>>(a);
-    if (launches) *launches += 2;
-    return cudaGetLastError();
+    int32_t *hist = hist_warp + lane;
+    bool stalled;
+#define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll>(row, n, nmax, rss, ord, q, coef16, active, hist, prog)
+    if (maxo <= 2) ALACGPU_LPC(2);
+    else if (maxo <= 4) ALACGPU_LPC(4);
+    else if (maxo <= 6) ALACGPU_LPC(6);
+    else if (maxo <= 8) ALACGPU_LPC(8);
+    else if (maxo <= 10) ALACGPU_LPC(10);
+    else if (maxo <= 12) ALACGPU_LPC(12);
+    else if (maxo <= 14) ALACGPU_LPC(14);
+    else if (maxo <= 16) ALACGPU_LPC(16);
+    else if (maxo <= 18) ALACGPU_LPC(18);
+    else if (maxo <= 20) ALACGPU_LPC(20);
+    else if (maxo <= 22) ALACGPU_LPC(22);
+    else if (maxo <= 24) ALACGPU_LPC(24);
+    else if (maxo <= 26) ALACGPU_LPC(26);
+    else if (maxo <= 28) ALACGPU_LPC(28);
+    else ALACGPU_LPC(30);
+#undef ALACGPU_LPC
+    if (kPoll && active && stalled) a.desc[f].status = FS_INTERNAL;   // never expected: see wait_avail
 }
 
 }  // namespace alacgpu

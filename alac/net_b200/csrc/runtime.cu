@@ -88,6 +88,7 @@ struct Slot {
     cudaStream_t st = nullptr;
     DevBuf<int32_t> planes;
     DevBuf<uint32_t> perm;        // K2 work list (2 entries per frame) + 1 count word at the end
+    DevBuf<uint32_t> progress;    // fused launch: per-stream hand-off words (2 per frame)
 };
 
 struct Device {
@@ -382,6 +383,7 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
     ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
     ca.perm = s.perm.p; ca.perm_count = s.perm.p + 2u * (size_t)d.chunk_frames;
+    ca.progress = s.progress.p;
     CU(cudaEventRecord(get_event(d, ev), s.st));
     if (with_k0) {
         K0Args ka{};
@@ -391,9 +393,18 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
         CU(launch_k0(ka, s.st, launches));
     }
     CU(cudaEventRecord(get_event(d, ev + 1), s.st));
-    if (with_decode) CU(launch_k1(ca, lanes_for(ctx), s.st, launches));
+    const bool fused = !(ctx->opts.flags & ALACGPU_FLAG_NO_FUSION);
+    if (with_decode) {
+        CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
+        if (fused) {
+            CU(cudaMemsetAsync(s.progress.p, 0, (size_t)c.n * 2u * sizeof(uint32_t), s.st));
+            CU(launch_k12(ca, lanes_for(ctx), s.st, launches));
+        } else {
+            CU(launch_k1(ca, lanes_for(ctx), s.st, launches));
+        }
+    }
     CU(cudaEventRecord(get_event(d, ev + 2), s.st));
-    if (with_decode) CU(launch_k2(ca, s.st, launches));
+    if (with_decode && !fused) CU(launch_k2(ca, s.st, launches));
     CU(cudaEventRecord(get_event(d, ev + 3), s.st));
     if (with_decode) CU(launch_k3(ca, s.st, launches));
     CU(cudaEventRecord(get_event(d, ev + 4), s.st));
@@ -426,6 +437,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
             for (int s = 0; s < slots_used; s++) {
                 CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
                 CU(d.slots[s].perm.reserve((size_t)cf * 2u + 4u));
+                CU(d.slots[s].progress.reserve((size_t)cf * 2u + 4u));
             }
         get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
         CU(cudaEventRecord(d.events[0], d.slots[0].st));
@@ -607,7 +619,7 @@ int32_t alacgpu_destroy(alacgpu_ctx *ctx)
         cudaDeviceSynchronize();
         d.arena.release(); d.refs.release(); d.cfgs.release(); d.desc.release(); d.coefs.release();
         d.expect_len.release(); d.frame_off.release(); d.scalars.release(); d.pcm.release();
-        for (Slot &s : d.slots) { s.planes.release(); s.perm.release(); if (s.st) cudaStreamDestroy(s.st); }
+        for (Slot &s : d.slots) { s.planes.release(); s.perm.release(); s.progress.release(); if (s.st) cudaStreamDestroy(s.st); }
         for (cudaEvent_t e : d.events) cudaEventDestroy(e);
         if (d.st_h2d) cudaStreamDestroy(d.st_h2d);
         if (d.st_d2h) cudaStreamDestroy(d.st_d2h);

@@ -229,7 +229,8 @@ def run_ours(args):
         pb.array[:] = np.frombuffer(t.mdat, dtype=np.uint8)
         pinned.append(pb)
 
-    dec = BatchDecoder(devices=[local], chunk_frames=args.chunk_frames, entropy_lanes=args.entropy_lanes)
+    dec = BatchDecoder(devices=[local], chunk_frames=args.chunk_frames, entropy_lanes=args.entropy_lanes,
+                       flags=(2 if args.no_fusion else 0))
     for t, pb in zip(tracks, pinned):
         dec.add_track(t.cfg, pb, t.stsz)
     total = dec.prepare()              # stage the mdat in HBM + header pre-pass: inputs resident
@@ -357,6 +358,7 @@ def main():
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--entropy-lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fusion", action="store_true", help="entropy and LPC as two kernels (A/B against the fused launch)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

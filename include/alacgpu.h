@@ -87,13 +87,15 @@ enum {
     ALACGPU_FRAME_BAD_RSS = 5,          /* sampleSize - 8*wastedBytes (+1) < 1                */
     ALACGPU_FRAME_HISTORY = 6,          /* Rice history wrapped negative (AlacFile.cs:229)    */
     ALACGPU_FRAME_RUN_OVERFLOW = 7,     /* zero run past the 16384-int scratch (AlacFile.cs:240-243) */
-    ALACGPU_FRAME_ORDER0_LONG = 8       /* order 0 with N > 4096 (AlacFile.cs:264-265)        */
+    ALACGPU_FRAME_ORDER0_LONG = 8,      /* order 0 with N > 4096 (AlacFile.cs:264-265)        */
+    ALACGPU_FRAME_INTERNAL = 9          /* decoder fault (fused-kernel hand-off timed out); never expected */
 };
 
 typedef struct alacgpu_ctx alacgpu_ctx;
 
 /* ---- options ------------------------------------------------------------- */
 #define ALACGPU_FLAG_KEEP_DEVICE_PCM 0x1u  /* keep decoded PCM resident in HBM after decode_all */
+#define ALACGPU_FLAG_NO_FUSION 0x2u        /* run entropy and LPC as two kernels instead of the fused, overlapped launch */
 
 typedef struct alacgpu_opts {
     uint32_t struct_size;      /* sizeof(alacgpu_opts), for forward compatibility       */
@@ -120,8 +122,8 @@ typedef struct alacgpu_track_cfg {
  * recorded on the streams the kernels were launched on. */
 typedef struct alacgpu_timing {
     float index_ms;        /* K0 header pre-pass, summed over chunks             */
-    float entropy_ms;      /* K1, summed over chunks                             */
-    float lpc_ms;          /* K2                                                 */
+    float entropy_ms;      /* K1, summed over chunks (fused launch: K1 and K2 together) */
+    float lpc_ms;          /* K2 (0 when fused into the entropy launch)          */
     float stereo_ms;       /* K3                                                 */
     float kernels_ms;      /* device pipeline span: first launch -> last kernel done (includes waits for H2D when streaming) */
     float h2d_ms;          /* mdat staging copies: first copy issued -> last done */

@@ -19,7 +19,7 @@ BUFFER_SIZE = 16384
 
 STATUS_NAMES = {
     0: "OK", 1: "BAD_TAG", 2: "PRED_TYPE", 3: "TOO_MANY_SAMPLES", 4: "OVERRUN",
-    5: "BAD_RSS", 6: "HISTORY", 7: "RUN_OVERFLOW", 8: "ORDER0_LONG",
+    5: "BAD_RSS", 6: "HISTORY", 7: "RUN_OVERFLOW", 8: "ORDER0_LONG", 9: "INTERNAL(gpu only)",
 }
 
 
