@@ -41,7 +41,7 @@ constexpr uint64_t kTrackAlign = 256;     // PCM start alignment of each track i
 // (at most 2 channels x 16384 symbols x 59 bits) until K1 flags the overrun at the end
 constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
-constexpr int kSlots = 8;
+constexpr int kSlots = 16;
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }

@@ -71,6 +71,17 @@ def test_chunking_and_lane_options_do_not_change_bytes(lanes, chunk, gen, oracle
     _assert_tracks_equal(tracks, got, status, oracle)
 
 
+@pytest.mark.parametrize("flags", [0, 2])
+def test_fused_and_two_kernel_paths_agree(flags, gen, oracle):
+    """ALACGPU_FLAG_NO_FUSION (2): entropy and LPC as two launches; default: one fused launch in which
+    the LPC warps consume residuals while the entropy lanes are still decoding"""
+    tracks = gen.make_config(2, scale=0.02) + gen.make_config(1, scale=0.1) + gen.make_config(3, scale=0.1)
+    got, status, tm = _decode(tracks, flags=flags)
+    _assert_tracks_equal(tracks, got, status, oracle)
+    # K0 + sort + K12 + K3 per chunk when fused; K0 + sort + K1 + K2 + K3 otherwise
+    assert tm["kernel_launches"] == tm["chunks"] * (5 if flags == 2 else 4)
+
+
 def test_resident_path_equals_streaming_path(gen, oracle):
     """prepare() + decode_all (inputs resident) vs decode_all alone (streams H2D chunk by chunk)"""
     from alac.net_b200 import BatchDecoder, host_checksum
@@ -149,7 +160,7 @@ def test_kmodifier_and_history_cookie_variants(gen, oracle):
     """non-default cookie parameters, incl. k above 16 (two-part Readbits) and tiny kmodifier"""
     rng = np.random.default_rng(21)
     tracks = []
-    for kmod, hm, ih in ((14, 40, 10), (6, 63, 200), (20, 40, 10), (2, 20, 0), (23, 255, 255)):
+    for kmod, hm, ih in ((14, 40, 10), (6, 63, 200), (20, 40, 10), (2, 20, 0), (23, 255, 255), (31, 40, 10), (1, 40, 10)):
         cfg = gen.TrackCfg(16, 2, 1024, hm, ih, kmod, 44100)
         n = 1024 * 6 + 100
         x = gen.make_signal(int(rng.integers(1, 1 << 30)), n, 16, 44100, 2).copy()
