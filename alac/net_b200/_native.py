@@ -22,7 +22,7 @@ FLAG_NO_FUSION = 0x2
 
 # every symbol include/alacgpu.h declares (tests check the export table against this)
 EXPORTS = [
-    "alacgpu_create", "alacgpu_destroy", "alacgpu_add_track", "alacgpu_clear_tracks",
+    "alacgpu_create", "alacgpu_destroy", "alacgpu_add_track", "alacgpu_add_track_offsets", "alacgpu_clear_tracks",
     "alacgpu_total_pcm_bytes", "alacgpu_prepare", "alacgpu_reindex", "alacgpu_decode_all", "alacgpu_read_frame", "alacgpu_track_count",
     "alacgpu_frame_count", "alacgpu_frame_samples", "alacgpu_track_pcm_bytes",
     "alacgpu_frame_status", "alacgpu_get_timing", "alacgpu_device_pcm", "alacgpu_pcm_checksum",
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
     L.alacgpu_create.argtypes = [i32p, C.c_int32, C.POINTER(Opts), C.POINTER(vp)]
     L.alacgpu_destroy.argtypes = [vp]
     L.alacgpu_add_track.argtypes = [vp, C.POINTER(TrackCfg), vp, C.c_uint64, C.c_uint64, vp, C.c_uint32, i32p]
+    L.alacgpu_add_track_offsets.argtypes = [vp, C.POINTER(TrackCfg), vp, C.c_uint64, vp, vp, C.c_uint32, i32p]
     L.alacgpu_clear_tracks.argtypes = [vp]
     L.alacgpu_total_pcm_bytes.argtypes = [vp, u64p]
     L.alacgpu_prepare.argtypes = [vp, u64p]

@@ -57,9 +57,29 @@ def build_host(force: bool = False) -> str:
     return LIB_HOST
 
 
+CLI = os.path.join(HERE, "cli")
+BIN_CLI = os.path.join(HERE, "alacgpu_decode")
+
+
+def build_cli(force: bool = False) -> str:
+    """alacgpu_decode: batch .m4a -> .wav tool over libalacgpu.so + the host mirror."""
+    src = os.path.join(CLI, "alacgpu_decode.cpp")
+    if not os.path.exists(src):
+        return ""
+    host_srcs = [os.path.join(HOST, s) for s in sorted(os.listdir(HOST)) if s.endswith(".cpp")]
+    deps = [src, LIB_GPU, *host_srcs] + [os.path.join(HOST, h) for h in os.listdir(HOST) if h.endswith(".hpp")]
+    if force or _newer(BIN_CLI, deps):
+        # the host mirror is compiled in (its shared library only exports the flat C test surface)
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", BIN_CLI, src, *host_srcs,
+               "-L", HERE, "-lalacgpu", "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread"]
+        subprocess.check_call(cmd)
+    return BIN_CLI
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_gpu(force, verbose)
     build_host(force)
+    build_cli(force)
 
 
 if __name__ == "__main__":

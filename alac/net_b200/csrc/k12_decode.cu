@@ -85,7 +85,7 @@ cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    const uint32_t warps = (a.n * 2u + 31u) / 32u;       // upper bound; warps past n_active exit at once
+    const uint32_t warps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;   // upper bound; warps past n_active exit at once
     k2_lpc<<<(warps + 3) / 4, kK2Threads, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -97,7 +97,7 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + 31u) / 32u;
+    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;
     k12_entropy_lpc<<<eblocks + (lwarps + 3) / 4, kK1Threads, 0, st>>>(a, lg, eblocks);
     if (launches) *launches += 1;
     return cudaGetLastError();

@@ -100,6 +100,9 @@ __device__ __forceinline__ void lpc_tap(int32_t &c, int32_t &E, uint32_t &acc, c
         : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "r"(negm));
 }
 
+#ifndef ALACGPU_LPC_STREAMS_PER_WARP
+#define ALACGPU_LPC_STREAMS_PER_WARP 32
+#endif
 constexpr int kK2Threads = 128;    // four LPC warps per block; blocks are issued heaviest first
 
 // All 32 lanes run this; `active` gates memory traffic only.
@@ -231,9 +234,10 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
 {
     const int lane = threadIdx.x & 31;
     const uint32_t n_active = a.perm_count[0];
-    const uint32_t idx = warp * 32u + (uint32_t)lane;
-    if (warp * 32u >= n_active) return;
-    const bool active = idx < n_active;
+    constexpr uint32_t SPW = ALACGPU_LPC_STREAMS_PER_WARP;
+    const uint32_t idx = warp * SPW + (uint32_t)lane;
+    if (warp * SPW >= n_active) return;
+    const bool active = idx < n_active && (uint32_t)lane < SPW;
     int n = 0, rss = 32, ord = 31, q = 0;
     const int16_t *coef16 = nullptr;
     int32_t *row = nullptr;

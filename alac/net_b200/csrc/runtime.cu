@@ -73,6 +73,7 @@ struct HostTrack {
     uint64_t first_frame;         // index into the global frame list
     uint32_t n_frames;
     uint64_t pcm_off, pcm_len;    // global (padded) layout
+    std::vector<uint64_t> offs;   // explicit byte offset of every frame (empty: frames are back to back)
 };
 
 struct HostCopy { const uint8_t *src; uint64_t dst, len; };
@@ -264,22 +265,34 @@ int32_t build_plan(alacgpu_ctx *ctx)
             const uint64_t a = std::max<uint64_t>(ht.first_frame, d.f_lo);
             const uint64_t b = std::min<uint64_t>(ht.first_frame + ht.n_frames, d.f_hi);
             if (a >= b) continue;
-            uint64_t off = ht.first_frame_offset;       // byte offset of frame a within the track's mdat
-            for (uint64_t f = ht.first_frame; f < a; f++) off += ctx->sizes[f];
+            // byte offset of every frame of [a, b) within the track's buffer: back to back from
+            // first_frame_offset (AlacContext.cs:194-195), or the caller's explicit table
+            std::vector<uint64_t> foff(b - a);
+            if (ht.offs.empty()) {
+                uint64_t off = ht.first_frame_offset;
+                for (uint64_t f = ht.first_frame; f < a; f++) off += ctx->sizes[f];
+                for (uint64_t f = a; f < b; f++) { foff[f - a] = off; off += ctx->sizes[f]; }
+            } else {
+                for (uint64_t f = a; f < b; f++) foff[f - a] = ht.offs[f - ht.first_frame];
+            }
+            uint64_t src_lo = ht.mdat_len, src_hi = 0;     // staged span: covers every frame (and any gap between them)
+            for (uint64_t f = a; f < b; f++) {
+                const uint64_t o = std::min(foff[f - a], ht.mdat_len);
+                const uint64_t e = std::min(foff[f - a] + ctx->sizes[f], ht.mdat_len);
+                if (e > o) { src_lo = std::min(src_lo, o); src_hi = std::max(src_hi, e); }
+            }
+            if (src_hi < src_lo) src_lo = src_hi = 0;
             const uint64_t base = align_up(used, 16);
-            const uint64_t src_lo = std::min(off, ht.mdat_len);
-            uint64_t cur = off;
             for (uint64_t f = a; f < b; f++) {
                 FrameRef r;
+                const uint64_t cur = foff[f - a];
                 const uint64_t avail = cur < ht.mdat_len ? ht.mdat_len - cur : 0;
                 r.len = (uint32_t)std::min<uint64_t>(ctx->sizes[f], avail);   // short read (MyStream.cs:47-52)
                 r.off = r.len ? base + (cur - src_lo) : base;
                 r.track = t;
                 d.h_refs[f - d.f_lo] = r;
                 compressed += r.len;
-                cur += ctx->sizes[f];
             }
-            const uint64_t src_hi = std::min(cur, ht.mdat_len);
             if (src_hi > src_lo) d.track_copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo});
             used = base + (src_hi - src_lo);
         }
@@ -629,9 +642,9 @@ int32_t alacgpu_destroy(alacgpu_ctx *ctx)
     return ALACGPU_OK;
 }
 
-int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const uint8_t *mdat, uint64_t mdat_len,
-                          uint64_t first_frame_offset, const uint32_t *frame_sizes, uint32_t n_frames,
-                          int32_t *track_id)
+static int32_t add_track_impl(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const uint8_t *mdat, uint64_t mdat_len,
+                              uint64_t first_frame_offset, const uint64_t *frame_offsets, const uint32_t *frame_sizes,
+                              uint32_t n_frames, int32_t *track_id)
 {
     if (!ctx || !cfg || (!mdat && mdat_len) || (!frame_sizes && n_frames)) return ALACGPU_ERR_INVALID_ARG;
     // "FIXME: unimplemented sample size" (AlacFile.cs:570-574, :713-715)
@@ -657,7 +670,9 @@ int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const 
     ctx->sizes.insert(ctx->sizes.end(), frame_sizes, frame_sizes + n_frames);
     ctx->out_len.reserve(ctx->out_len.size() + n_frames);
     ctx->frame_off.reserve(ctx->frame_off.size() + n_frames);
+    if (frame_offsets) t.offs.assign(frame_offsets, frame_offsets + n_frames);
     for (uint32_t f = 0; f < n_frames; f++) {
+        if (frame_offsets) off = frame_offsets[f];
         const uint64_t avail = off < mdat_len ? mdat_len - off : 0;
         const uint64_t len = std::min<uint64_t>(frame_sizes[f], avail);
         const uint32_t bytes = frame_pcm_bytes(*cfg, mdat + std::min(off, mdat_len), len);
@@ -673,6 +688,21 @@ int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const 
     invalidate(ctx);
     if (track_id) *track_id = (int32_t)ctx->tracks.size() - 1;
     return ALACGPU_OK;
+}
+
+int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const uint8_t *mdat, uint64_t mdat_len,
+                          uint64_t first_frame_offset, const uint32_t *frame_sizes, uint32_t n_frames,
+                          int32_t *track_id)
+{
+    return add_track_impl(ctx, cfg, mdat, mdat_len, first_frame_offset, nullptr, frame_sizes, n_frames, track_id);
+}
+
+int32_t alacgpu_add_track_offsets(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, const uint8_t *file, uint64_t file_len,
+                                  const uint64_t *frame_offsets, const uint32_t *frame_sizes, uint32_t n_frames,
+                                  int32_t *track_id)
+{
+    if (!frame_offsets && n_frames) return ALACGPU_ERR_INVALID_ARG;
+    return add_track_impl(ctx, cfg, file, file_len, 0, frame_offsets, frame_sizes, n_frames, track_id);
 }
 
 int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx)

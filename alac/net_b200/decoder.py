@@ -109,6 +109,23 @@ class BatchDecoder:
         self.n_frames += int(stsz.size)
         return tid.value
 
+    def add_track_offsets(self, cfg, file_bytes, frame_offsets, stsz) -> int:
+        """frames at explicit byte offsets of `file_bytes` (chunked / gapped containers)."""
+        stsz = np.ascontiguousarray(stsz, dtype=np.uint32)
+        offs = np.ascontiguousarray(frame_offsets, dtype=np.uint64)
+        assert offs.size == stsz.size
+        arr = np.frombuffer(file_bytes, dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else file_bytes
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        self._keep += [arr, stsz, offs]
+        tid = C.c_int32(-1)
+        c = _cfg_struct(cfg)
+        rc = self._L.alacgpu_add_track_offsets(self._h, C.byref(c), arr.ctypes.data if arr.size else None, arr.size,
+                                               offs.ctypes.data if offs.size else None,
+                                               stsz.ctypes.data if stsz.size else None, stsz.size, C.byref(tid))
+        self._check(rc, "alacgpu_add_track_offsets")
+        self.n_frames += int(stsz.size)
+        return tid.value
+
     def clear(self):
         self._check(self._L.alacgpu_clear_tracks(self._h), "alacgpu_clear_tracks")
         self._keep = []

@@ -78,6 +78,37 @@ def _as_array(data) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
+def iso_demux(m4a) -> dict:
+    """alacnet::IsoDemux: tolerant ISO-BMFF demux -> cookie + per-frame (offset, size, duration)."""
+    from . import _native as N
+    L = load()
+    a = _as_array(m4a)
+    cap = max(1, a.size // 4)
+    cfg = N.TrackCfg()
+    offs = np.zeros(cap, dtype=np.uint64)
+    sizes = np.zeros(cap, dtype=np.uint32)
+    durs = np.zeros(cap, dtype=np.uint32)
+    n = C.c_uint32(0)
+    total = C.c_uint64(0)
+    L.alacnet_iso_demux.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    rc = L.alacnet_iso_demux(a.ctypes.data, a.size, C.byref(cfg), offs.ctypes.data, sizes.ctypes.data, durs.ctypes.data,
+                             cap, C.byref(n), C.byref(total))
+    if rc != 0:
+        raise IOException("no ALAC audio track found")
+    k = n.value
+    return {"cfg": cfg, "offsets": offs[:k].copy(), "stsz": sizes[:k].copy(), "durations": durs[:k].copy(),
+            "total_samples": total.value}
+
+
+def wav_header(rate: int, bits: int, channels: int, pcm_bytes: int) -> bytes:
+    L = load()
+    buf = (C.c_uint8 * 44)()
+    L.alacnet_wav_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+    L.alacnet_wav_header(rate, bits, channels, pcm_bytes, buf)
+    return bytes(buf)
+
+
 def demux(m4a) -> dict:
     """QtMovieT.ReadHeader over an in-memory file (host only, no GPU)."""
     L = load()

@@ -21,7 +21,7 @@ namespace ALACdotNET.Decoder.Gpu
     internal enum AlacGpuFrameStatus : int
     {
         Ok = 0, BadTag = 1, PredType = 2, TooManySamples = 3, Overrun = 4,
-        BadRss = 5, History = 6, RunOverflow = 7, Order0Long = 8
+        BadRss = 5, History = 6, RunOverflow = 7, Order0Long = 8, Internal = 9
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -70,6 +70,7 @@ namespace ALACdotNET.Decoder.Gpu
         [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_create(int* deviceIds, int nDevices, ref AlacGpuOpts opts, out AlacGpuHandle ctx);
         [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_destroy(IntPtr ctx);
         [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_add_track(AlacGpuHandle ctx, ref AlacGpuTrackCfg cfg, byte* mdat, ulong mdatLen, ulong firstFrameOffset, uint* frameSizes, uint nFrames, out int trackId);
+        [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_add_track_offsets(AlacGpuHandle ctx, ref AlacGpuTrackCfg cfg, byte* file, ulong fileLen, ulong* frameOffsets, uint* frameSizes, uint nFrames, out int trackId);
         [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_clear_tracks(AlacGpuHandle ctx);
         [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_total_pcm_bytes(AlacGpuHandle ctx, out ulong total);
         [DllImport(Lib, CallingConvention = Cc)] public static extern int alacgpu_prepare(AlacGpuHandle ctx, out ulong total);

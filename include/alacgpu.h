@@ -160,6 +160,14 @@ ALACGPU_API int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg 
                                       uint64_t first_frame_offset,
                                       const uint32_t *frame_sizes, uint32_t n_frames,
                                       int32_t *track_id);
+/* Same, for containers whose frames are NOT back to back: frame i occupies
+ * frame_sizes[i] bytes at frame_offsets[i] of `file` (the chunk-offset addressing
+ * AlacContext.SetPosition derives from stco x stsc x stsz, AlacContext.cs:262-295;
+ * co64 offsets fit too).  Used by the tolerant demuxer. */
+ALACGPU_API int32_t alacgpu_add_track_offsets(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg,
+                                              const uint8_t *file, uint64_t file_len,
+                                              const uint64_t *frame_offsets, const uint32_t *frame_sizes,
+                                              uint32_t n_frames, int32_t *track_id);
 /* Forget all tracks but keep device / pinned allocations for reuse. */
 ALACGPU_API int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx);
 

@@ -118,3 +118,49 @@ def test_filereader_position_roundtrip_like_the_demo(gen, oracle):
     pos_samples = (rd.Length // 2) // 4
     n = rd.Read(buf, 0, 16)
     assert buf[:n].tobytes() == ref[pos_samples * 4:pos_samples * 4 + 16]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(co64=True, mdat_first=True, large_mdat=True), dict(split_stts=True, chunk_frames=3, gap=0)])
+def test_tolerant_demux_decodes_chunked_files(kw, gen, oracle):
+    """IsoDemux + alacgpu_add_track_offsets: frames addressed through stsc x stco/co64 x stsz with junk
+    between chunks (the reference would read the junk as frame data, AlacContext.cs:194-195)"""
+    from alac.net_b200 import BatchDecoder, hostmirror as H
+    tracks = [gen.make_config(1, scale=0.05)[0], gen.make_config(2, scale=0.004)[0]]
+    with BatchDecoder(devices=[0]) as dec:
+        for t in tracks:
+            m4a = gen.mux_m4a_ex(t, **kw)
+            d = H.iso_demux(m4a)
+            dec.add_track_offsets(d["cfg"], m4a, d["offsets"], d["stsz"])
+        pcm, off, ln, status = dec.decode_all()
+        assert (status == 0).all()
+        for t, o, l in zip(tracks, off, ln):
+            ref = oracle.decode_track(oracle.cfg_from(t.cfg), t.mdat, t.stsz)[0]
+            assert pcm[int(o):int(o + l)].tobytes() == ref
+
+
+def test_cli_batch_to_wav(tmp_path, gen, oracle):
+    """alacgpu_decode: two files in one batch -> two .wav files whose data chunks equal the oracle's PCM"""
+    import os, subprocess
+    from alac.net_b200 import build
+    tracks = [gen.make_config(1, scale=0.03)[0], gen.make_config(2, scale=0.003)[0]]
+    paths = []
+    for i, t in enumerate(tracks):
+        p = tmp_path / f"in{i}.m4a"
+        p.write_bytes(gen.mux_m4a_ex(t, co64=bool(i)))
+        paths.append(str(p))
+    outdir = tmp_path / "out"
+    outdir.mkdir()
+    r = subprocess.run([build.BIN_CLI, "-o", str(outdir), *paths], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    for i, t in enumerate(tracks):
+        wav = (outdir / f"in{i}.wav").read_bytes()
+        ref = oracle.decode_track(oracle.cfg_from(t.cfg), t.mdat, t.stsz)[0]
+        assert wav[:4] == b"RIFF" and wav[44:] == ref
+    # --strict = the reference's grammar: rejects the chunked file, accepts the plain one
+    plain = tmp_path / "plain.m4a"
+    plain.write_bytes(gen.mux_m4a(tracks[0]))
+    r = subprocess.run([build.BIN_CLI, "--strict", "-o", str(tmp_path / "p.wav"), str(plain)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "p.wav").read_bytes()[44:] == oracle.decode_track(oracle.cfg_from(tracks[0].cfg), tracks[0].mdat, tracks[0].stsz)[0]
+    r = subprocess.run([build.BIN_CLI, "--strict", "-o", str(tmp_path / "q.wav"), paths[0]], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "QuickTime movie headers" in r.stderr

@@ -185,3 +185,44 @@ def test_uniform_stsz(built, gen):
     assert len(set(t.stsz.tolist())) == 1
     d = H.demux(gen.mux_m4a(t, uniform_stsz=True))
     assert d["status"] == 1 and np.array_equal(d["stsz"], t.stsz)
+
+
+# ---- tolerant demux and the WAV writer ------------------------------------
+VARIANTS = [dict(), dict(co64=True), dict(mdat_first=True), dict(split_stts=True, chunk_frames=3, gap=0),
+            dict(large_mdat=True, mdat_first=True, co64=True), dict(extra_atoms=False, chunk_frames=1, gap=5)]
+
+
+@pytest.mark.parametrize("kw", VARIANTS)
+def test_iso_demux_resolves_chunked_layouts(kw, built, gen):
+    from alac.net_b200 import hostmirror as H
+    t = gen.make_config(1, scale=0.03)[0]
+    m4a = gen.mux_m4a_ex(t, **kw)
+    d = H.iso_demux(m4a)
+    cfg = d["cfg"]
+    assert (cfg.sample_size, cfg.num_channels, cfg.max_samples_per_frame, cfg.sample_rate) == (16, 2, 4096, 44100)
+    assert (cfg.rice_history_mult, cfg.rice_initial_history, cfg.rice_kmodifier) == (40, 10, 14)
+    assert np.array_equal(d["stsz"], t.stsz) and np.array_equal(d["durations"], t.frame_samples)
+    assert d["total_samples"] == t.n_sample_frames
+    offs = np.concatenate([[0], np.cumsum(t.stsz.astype(np.int64))])
+    for f in (0, 1, t.n_frames // 2, t.n_frames - 1):
+        o = int(d["offsets"][f])
+        assert m4a[o:o + int(t.stsz[f])] == t.mdat[offs[f]:offs[f + 1]]
+    # the reference's grammar rejects every one of these layouts (unknown atoms, co64, mdat first, ...)
+    if kw.get("extra_atoms", True) or kw.get("co64") or kw.get("mdat_first"):
+        assert H.demux(m4a)["status"] in (0, 3)
+    # and the plain layout parses identically through both demuxers
+    plain = gen.mux_m4a(t)
+    a, b = H.iso_demux(plain), H.demux(plain)
+    assert np.array_equal(a["stsz"], b["stsz"]) and int(a["offsets"][0]) == b["mdat_pos"]
+
+
+def test_wav_header_fields(built):
+    import struct
+    from alac.net_b200 import hostmirror as H
+    h = H.wav_header(96000, 24, 2, 345_600_000)
+    assert h[:4] == b"RIFF" and h[8:16] == b"WAVEfmt " and h[36:40] == b"data"
+    riff, = struct.unpack("<I", h[4:8])
+    fmt_len, tag, ch, rate, bps, align, bits = struct.unpack("<IHHIIHH", h[16:36])
+    data, = struct.unpack("<I", h[40:44])
+    assert (fmt_len, tag, ch, rate, bps, align, bits) == (16, 1, 2, 96000, 96000 * 6, 6, 24)
+    assert data == 345_600_000 and riff == data + 36

@@ -435,6 +435,80 @@ def mux_m4a(track: Track, mdat_first: bool = False, free_atom: bool = False,
     return ftyp + moov_with(off) + free + mdat
 
 
+def mux_m4a_ex(track: Track, chunk_frames: int = 7, gap: int = 13, co64: bool = False, mdat_first: bool = False,
+               extra_atoms: bool = True, split_stts: bool = False, large_mdat: bool = False) -> bytes:
+    """A container the REFERENCE's demuxer rejects but real encoders write: frames grouped into chunks
+    of `chunk_frames` with `gap` junk bytes between chunks (stsc/stco addressing), optional co64, mdat
+    before moov, 64-bit mdat size, unknown atoms (wide, meta, udta children, sgpd inside stbl) and one
+    stts run per frame.  Exercises alacnet::IsoDemux + alacgpu_add_track_offsets (SURVEY.md 8(f) item 3)."""
+    cfg = track.cfg
+    nf = track.n_frames
+    offs = np.concatenate([[0], np.cumsum(track.stsz.astype(np.int64))])
+    # mdat payload: chunks separated by junk
+    payload = bytearray()
+    chunk_rel = []
+    for c0 in range(0, nf, chunk_frames):
+        c1 = min(nf, c0 + chunk_frames)
+        payload += bytes([0xEE]) * gap
+        chunk_rel.append(len(payload))
+        payload += track.mdat[offs[c0]:offs[c1]]
+    payload += bytes([0xEE]) * gap
+    n_chunks = len(chunk_rel)
+    last = nf - chunk_frames * (n_chunks - 1)
+    ftyp = _atom(b"ftyp", b"M4A " + struct.pack(">I", 512) + b"M4A mp42isom")
+    wide = _atom(b"wide", b"") if extra_atoms else b""
+    mvhd = _atom(b"mvhd", bytes(100))
+    tkhd = _atom(b"tkhd", bytes(84))
+    mdhd = _atom(b"mdhd", bytes(24))
+    hdlr = _atom(b"hdlr", bytes(4) + bytes(4) + b"soun" + bytes(12) + b"SoundHandler\x00")
+    smhd = _atom(b"smhd", bytes(8))
+    dinf = _atom(b"dinf", _atom(b"dref", bytes(4) + struct.pack(">I", 1) + _atom(b"url ", b"\x00\x00\x00\x01")))
+    alac = _atom(b"alac", bytes(4) + alac_cookie(cfg, int(track.stsz.max()) if nf else 0))
+    entry = (bytes(6) + struct.pack(">H", 1) + bytes(8) + struct.pack(">HH", cfg.num_channels, cfg.sample_size)
+             + bytes(4) + struct.pack(">I", (cfg.sample_rate & 0xFFFF) << 16) + alac)
+    stsd = _atom(b"stsd", bytes(4) + struct.pack(">I", 1) + _atom(b"alac", entry))
+    if split_stts:
+        runs = [[1, int(d)] for d in track.frame_samples.tolist()]
+    else:
+        runs = []
+        for d in track.frame_samples.tolist():
+            if runs and runs[-1][1] == d:
+                runs[-1][0] += 1
+            else:
+                runs.append([1, d])
+    stts = _atom(b"stts", bytes(4) + struct.pack(">I", len(runs)) + b"".join(struct.pack(">II", c, d) for c, d in runs))
+    stsc_runs = [(1, chunk_frames, 1)]
+    if last != chunk_frames:
+        stsc_runs.append((n_chunks, last, 1))
+    stsc = _atom(b"stsc", bytes(4) + struct.pack(">I", len(stsc_runs)) + b"".join(struct.pack(">III", *r) for r in stsc_runs))
+    stsz = _atom(b"stsz", bytes(4) + struct.pack(">II", 0, nf) + track.stsz.astype(">u4").tobytes())
+    sgpd = _atom(b"sgpd", bytes(12)) if extra_atoms else b""
+    udta = _atom(b"udta", _atom(b"meta", bytes(4) + _atom(b"hdlr", bytes(25)) + _atom(b"ilst", b""))) if extra_atoms else b""
+    mdat_hdr = 16 if large_mdat else 8
+
+    def moov_with(base: int) -> bytes:
+        if co64:
+            stco = _atom(b"co64", bytes(4) + struct.pack(">I", n_chunks) + b"".join(struct.pack(">Q", base + r) for r in chunk_rel))
+        else:
+            stco = _atom(b"stco", bytes(4) + struct.pack(">I", n_chunks) + b"".join(struct.pack(">I", base + r) for r in chunk_rel))
+        stbl = _atom(b"stbl", stsd + stts + sgpd + stsz + stsc + stco)      # not the reference's order either
+        minf = _atom(b"minf", smhd + dinf + stbl)
+        mdia = _atom(b"mdia", mdhd + hdlr + minf)
+        trak = _atom(b"trak", tkhd + _atom(b"edts", _atom(b"elst", bytes(16))) + mdia)
+        return _atom(b"moov", mvhd + trak + udta)
+
+    if large_mdat:
+        mdat = struct.pack(">I", 1) + b"mdat" + struct.pack(">Q", 16 + len(payload)) + bytes(payload)
+    else:
+        mdat = _atom(b"mdat", bytes(payload))
+    if mdat_first:
+        base = len(ftyp) + len(wide) + mdat_hdr
+        return ftyp + wide + mdat + moov_with(base)
+    moov_len = len(moov_with(0))
+    base = len(ftyp) + len(wide) + moov_len + mdat_hdr
+    return ftyp + wide + moov_with(base) + mdat
+
+
 if __name__ == "__main__":  # small smoke: write config 1 to a file
     import sys
     tr = make_config(1, scale=float(sys.argv[2]) if len(sys.argv) > 2 else 0.05)[0]
