@@ -8,35 +8,33 @@
 // length depends on the running history, and channel B starts at the bit
 // where channel A ends (AlacFile.cs:643 then :653 share one cursor).  So the
 // unit of parallelism is the FRAME: one lane per frame, channel A then B, and
-// the kernel's run time is (symbols per frame) x (cycles per symbol) whatever
-// the batch size.  Everything here serves a short per-symbol dependency chain:
+// the stage's run time is (symbols per frame) x (cycles per symbol) whatever
+// the batch size.  Everything here serves a short per-symbol path:
 //
-//   * ONE BIT FIELD PER LOOP ITERATION PER LANE, whatever its kind.  The
-//     reference decodes three kinds of field: the sample's Rice symbol, the
-//     zero-run length symbol that follows a small history (:231-249), and the
-//     raw field after nine 1-bits (:198-202).  A lane that hit one of the rare
-//     kinds simply spends an extra iteration on it (two state bits say what
-//     the next field is); the other lanes do not wait for it as they would if
-//     the rare paths were divergent branches.  Lanes therefore drift apart by
-//     a few percent, so each lane writes through its own output counter:
-//     residuals go to a conflict-free shared-memory ring ([slot][lane]) and
-//     leave it as 16-byte stores into the lane's row of the stream-major plane
-//     at warp-uniform flush points (every eight iterations).  A zero run emits
-//     one zero per iteration.
-//   * The loop body is one small straight-line block (it must stay in the
-//     instruction cache: a lone warp per scheduler cannot hide fetch misses).
-//     All state changes are selects; the operands that depend on the field
-//     just read (new cursor, new history) are one or two instructions after it:
-//     the alternatives (skip k or k+1 bits, raw vs Rice value, keep vs update
-//     the history) are computed beside the field extraction and chosen late.
+//   * Lock step over the OUTPUT index: a lane inside a zero run emits its
+//     zeros one per step instead of jumping ahead (AlacFile.cs:238-245 writes
+//     them in a burst), so the common case is one straight-line block for
+//     every lane and four residuals leave the lane as one 16-byte store into
+//     its own row of the stream-major plane.
+//   * The operands that depend on the field just read (new cursor, new
+//     history) are one or two instructions after it: the field is
+//     (w >> (p - k)) & m with p = bfind(~w); value + signModifier = A + max(e,1)
+//     with A = x*m + signModifier - 1 computed beside it; the history is
+//     max(e,1)*mult + (A*mult + h - ((h*mult) >> 9)).
+//   * The rare paths -- the raw field after nine 1-bits (:198-202) and the
+//     zero-run length symbol after a small history (:231-249) -- sit in one
+//     plain divergent block.  (Measured alternatives, all byte-exact: a warp
+//     vote in front of the block costs ~100 cycles per sample in WARPSYNC/VOTE;
+//     a per-lane "one field per iteration" state machine without lock step
+//     needs twice the instructions per sample; an 8x unrolled body misses the
+//     instruction cache.  See DESIGN.md section 3.)
 //   * bitstream: each lane owns a 256-byte ring in shared memory, filled by
-//     16-byte cp.async copies at the flush points (no register ever waits on
+//     16-byte cp.async copies every eight samples (no register ever waits on
 //     HBM); the cursor keeps two byte-swapped words in registers plus one
 //     prefetched word, so the 32-bit window at the cursor is ONE funnel shift.
-//   * unary prefix = bfind(~window); the k extra bits come from the same
-//     window: k <= 22 always ((history >> 9) + 3 < 2^23; zero-run k <= 16), so
-//     prefix + terminator + k bits fit 32.  "Read k bits, un-read one if the
-//     value is <= 1" (AlacFile.cs:205-210) is "consume k-1 bits".
+//   * k <= 22 always ((history >> 9) + 3 < 2^23; zero-run k <= 16), so prefix +
+//     terminator + k bits fit the 32-bit window.  "Read k bits, un-read one if
+//     the value is <= 1" (AlacFile.cs:205-210) is "consume k-1 bits".
 //   * CountLeadingZeros' clz(0) == 40 quirk (AlacFile.cs:190) is kept in the
 //     zero-run k, the only place a zero argument can reach it.
 //
@@ -52,7 +50,7 @@ namespace alacgpu {
 
 constexpr int kRingChunks = 16;              // 256 B of bitstream per lane
 constexpr int kRingBytes = kRingChunks * 16;
-constexpr int kFlushEvery = 8;               // iterations between flush / top-up points
+constexpr int kFlushEvery = 8;               // samples between ring top-ups
 constexpr int kK1Threads = 128;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr)
@@ -68,10 +66,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t smem_addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts32(uint32_t smem_addr, int32_t v)
-{
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
-}
 // position of the most significant 1 bit (31 - clz), -1 for 0
 __device__ __forceinline__ int flo(uint32_t v)
 {
@@ -80,10 +74,11 @@ __device__ __forceinline__ int flo(uint32_t v)
     return r;
 }
 
-// Bit cursor over the lane's ring.  A lane consumes at most 32 bits per iteration, i.e. at
-// most two 16-byte chunks per flush period, and reads two words ahead of its cursor:
-// everything it touches during a period was requested at least one period earlier, so the
-// wait for the PREVIOUS period's copies is normally free.
+// Bit cursor over the lane's ring.  A lane consumes at most 59 bits per sample (9 ones + 25
+// raw bits, plus a zero-run symbol of 9 + 16), i.e. < 4 chunks per period of eight samples,
+// and reads two words ahead of its cursor: everything it touches during a period lies within
+// chunk(cursor at the previous top-up) + 4 + 4 + 1 < kRingChunks and was requested at least
+// one period earlier, so the wait for the PREVIOUS period's copies is normally free.
 struct BitCursor {
     const uint8_t *base;    // 16-byte aligned global address of chunk 0
     uint32_t ring;          // shared-space byte address of this lane's ring (256-byte aligned)
@@ -166,8 +161,8 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     const int S = 1 << lanes_log2;
     const uint32_t gw = (block * kK1Threads + threadIdx.x) >> 5;
     const uint32_t slot = gw * (uint32_t)S + (uint32_t)lane;
-    // Every lane stays in the loops (their exits are warp votes); a lane without work runs
-    // with n == 0 and commits nothing.
+    // Every lane stays in the loops (warp-uniform trip counts); a lane without work runs with
+    // n == 0 and commits nothing.
     bool work = lane < S && slot < a.n;
     const uint64_t f = a.f0 + (work ? slot : 0u);
     const FrameDesc d = a.desc[f];

@@ -266,3 +266,22 @@ def test_two_devices_in_one_context(gen, oracle):
         assert dec.checksum() == host_checksum(pcm[:dec.total_pcm_bytes()])
         f = tracks[1].n_frames - 1
         assert dec.read_frame(1, f) == got[1][len(got[1]) - tracks[1].frame_samples[f] * 6:]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_payload_fuzz_matches_oracle(seed, gen, oracle):
+    """valid headers + random payload bits (tests/test_fuzz_oracle_model.py): PCM and status words of
+    every frame must equal the oracle's, OK or not"""
+    from tests.test_fuzz_oracle_model import random_frame
+    rng = np.random.default_rng(7000 + seed)
+    tracks = []
+    for ss, cch, max_n, hm, ih, kmod in ((16, 2, 200, 40, 10, 14), (24, 2, 64, 40, 10, 14), (16, 1, 200, 255, 255, 20),
+                                          (24, 1, 16, 4, 0, 6), (16, 2, 4096, 40, 10, 14)):
+        frames = [random_frame(rng, ss, max_n)[0] for _ in range(150 if max_n < 4096 else 12)]
+        cfg = gen.TrackCfg(ss, cch, max_n, hm, ih, kmod, 44100)
+        stsz = np.array([len(f) for f in frames], dtype=np.uint32)
+        tracks.append(gen.Track(cfg, b"".join(frames), stsz, np.zeros(len(frames), np.int32), b""))
+    for flags in (0, 2):
+        got, status, _ = _decode(tracks, flags=flags)
+        _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
+        assert (status == 0).any() and (status != 0).any()
