@@ -69,9 +69,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t smem_addr)
 // position of the most significant 1 bit (31 - clz), -1 for 0
 __device__ __forceinline__ int flo(uint32_t v)
 {
-    int r;
-    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
-    return r;
+    return 31 - __clz((int)v);
 }
 
 // Bit cursor over the lane's ring.  A lane consumes at most 59 bits per sample (9 ones + 25
@@ -82,7 +80,10 @@ __device__ __forceinline__ int flo(uint32_t v)
 struct BitCursor {
     const uint8_t *base;    // 16-byte aligned global address of chunk 0
     uint32_t ring;          // shared-space byte address of this lane's ring (256-byte aligned)
-    uint32_t ra;            // shared-space address of the next word to prefetch into `nn`
+    const uint32_t *ringw;  // the same ring as 64 words (plain pointer: the per-sample refill below is an
+                            // ordinary predicated LDS -- an `asm volatile` there makes the compiler
+                            // re-converge the whole warp (WARPSYNC.ALL) after every divergent block)
+    uint32_t rw;            // index (mod 64) of the next ring word to prefetch into `nn`
     uint32_t cur, nxt;      // byte-swapped words holding bits [32*w, 32*w+64) at the cursor's word w
     uint32_t nn;            // raw word w+2
     uint32_t off;           // cursor bit within `cur`, 0..31
@@ -99,11 +100,12 @@ struct BitCursor {
         }
         cp_async_commit();
     }
-    __device__ __forceinline__ void init(const uint8_t *arena, uint64_t abs_bit, uint32_t ring_addr)
+    __device__ __forceinline__ void init(const uint8_t *arena, uint64_t abs_bit, const uint8_t *ring_ptr)
     {
         const uint64_t byte = abs_bit >> 3;
         base = arena + (byte & ~15ull);
-        ring = ring_addr;
+        ring = (uint32_t)__cvta_generic_to_shared(ring_ptr);
+        ringw = reinterpret_cast<const uint32_t *>(ring_ptr);
         const uint32_t pos = (uint32_t)(byte & 15) * 8u + (uint32_t)(abs_bit & 7);
         word0 = pos >> 5;
         off = off0 = pos & 31;
@@ -114,11 +116,13 @@ struct BitCursor {
         cur = bswap32(lds32(ring + ((word0 * 4u) & (kRingBytes - 1))));
         nxt = bswap32(lds32(ring + (((word0 + 1) * 4u) & (kRingBytes - 1))));
         nn = lds32(ring + (((word0 + 2) * 4u) & (kRingBytes - 1)));
-        ra = ring + (((word0 + 3) * 4u) & (kRingBytes - 1));
+        rw = (word0 + 3) & (kRingBytes / 4 - 1);
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, off); }
 
-    // move the cursor to bit t (0..63) of the current word pair
+    // move the cursor to bit t (0..63) of the current word pair.  The word prefetched here was
+    // requested two top-ups ago (see above), so the load needs no ordering against the current
+    // period's cp.async wait beyond the compiler barrier that wait already is.
     __device__ __forceinline__ void seek(uint32_t t)
     {
         const bool rf = t >= 32u;
@@ -127,17 +131,8 @@ struct BitCursor {
         // nxt = rf ? bswap(nn) : nxt in one PRMT: selector 0x0123 reverses nn, 0x7654 passes nxt
         nxt = __byte_perm(nn, nxt, rf ? 0x0123u : 0x7654u);
         words += rf ? 1u : 0u;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.u32 p, %2, 0;\n\t"
-            "@p ld.shared.u32 %0, [%1];\n\t"
-            "@p add.u32 %1, %1, 4;\n\t"
-            "@p lop3.b32 %1, %1, 255, %3, 0xEA;\n\t"      // (ra & 255) | ring
-            "}"
-            : "+r"(nn), "+r"(ra)
-            : "r"((uint32_t)rf), "r"(ring)
-            : "memory");
+        if (rf) nn = ringw[rw];
+        rw = (rw + (rf ? 1u : 0u)) & (kRingBytes / 4 - 1);
     }
     __device__ __forceinline__ uint32_t consumed() const { return words * 32u + off - off0; }
 };
@@ -178,8 +173,14 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     const int nmax = __reduce_max_sync(0xffffffffu, n);
 
     BitCursor br;
-    br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull,
-            (uint32_t)__cvta_generic_to_shared(ring_smem) + threadIdx.x * (uint32_t)kRingBytes);
+    br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull, ring_smem + threadIdx.x * (uint32_t)kRingBytes);
+
+    // Loop counters are kept in ordinary (per-thread) registers on purpose: if they live in the
+    // uniform datapath, ptxas must re-converge the warp (WARPSYNC.ALL, ~50 cycles) after the
+    // divergent rare-path block of EVERY sample before it may touch them again.
+    int lane_opaque;
+    asm("mov.u32 %0, %1;" : "=r"(lane_opaque) : "r"(lane));
+    const int zero = lane_opaque - lane;
 
     uint8_t status = FS_OK;
     for (int c = 0; c < ech_max; c++) {
@@ -193,7 +194,7 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
         uint32_t m0 = (1u << k) - 1u;
         uint32_t *prog = a.progress + ((uint64_t)(work ? slot : 0u) * 2u + (uint32_t)c);
 
-        for (int i0 = 0; i0 < nmax; i0 += kFlushEvery) {
+        for (int i0 = zero; i0 < nmax; i0 += kFlushEvery) {
             br.top_up();
             cp_async_wait<1>();                  // everything but the group just committed
 #pragma unroll 1
