@@ -50,3 +50,35 @@ def reduce_step(dist, device, ms_local: float, units_local: float):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPU cores of the NUMA node the GPU hangs off, BEFORE any pinned
+    buffer is allocated (first touch then places the staging buffers next to the GPU's PCIe root).
+    With one rank per GPU the end-to-end path is bound by host<->device copies; on a two-socket box
+    half of the ranks otherwise push every byte over the socket interconnect.  Best effort: returns
+    what it did, never raises."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info = {"numa_node": node, "cpus": len(use)}
+    except Exception:
+        pass
+    return info

@@ -247,6 +247,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the decode path has no CPU fallback)")
     torch.cuda.set_device(local)
+    from alac.net_b200.shard import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"numa_node": None, "cpus": None}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -370,6 +372,7 @@ def run_ours(args):
                 "parallelism": f"frame-range shards, {world} rank(s), no collective",
                 "parity": "bit-exact vs encoder input and device checksum, checked in this run",
                 "fused_entropy_lpc": fused,
+                "numa_bind": numa,
             },
             "device_ms_per_step": dev_ms_max,
             "stage_ms": stage,
@@ -417,6 +420,7 @@ def main():
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--entropy-lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--batch-tracks", type=int, default=64, help="tracks of the configs[3]-shaped throughput leg (0 = skip)")
     ap.add_argument("--no-fusion", action="store_true", help="entropy and LPC as two kernels (A/B against the fused launch)")
     args = ap.parse_args()
