@@ -66,7 +66,8 @@ struct __align__(16) FrameDesc {
     uint8_t order[2];
     uint8_t quant[2];
     uint8_t rice_mod[2];
-    uint8_t pad[6];
+    uint8_t status0;       // K0's verdict, never changed afterwards (`status` may be raised by the entropy stage)
+    uint8_t pad[5];
 };
 static_assert(sizeof(FrameDesc) == 32, "FrameDesc is 32 bytes");
 

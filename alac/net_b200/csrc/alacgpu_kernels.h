@@ -45,13 +45,20 @@ struct ChunkArgs {
     uint32_t max_sf;               // most sample-frames any frame of the batch emits
     uint32_t *perm;                // K2 work list: active stream ids sorted by descending order (2n entries)
     uint32_t *perm_count;          // [0] = number of entries of perm
-    uint32_t *progress;            // fused launch: residuals published per stream (2n entries, zeroed before the launch)
+    uint32_t *progress;            // fused launch: residuals published per stream by the entropy lanes (2n entries, zeroed before the launch)
+    uint32_t *lpc_done;            // fused launch: predicted samples published per stream by the LPC lanes (2n entries, zeroed)
+    uint32_t *pack_next;           // fused launch: next pack task (zeroed)
+    uint8_t *lpc_flag;             // per stream: 1 if the stream is on the LPC work list (written by the sort)
 };
 cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);   // K2 / K12 work list
 cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);
 // fused entropy + LPC (one launch, LPC warps consume residuals as the entropy lanes publish them)
 cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
+// fused entropy + LPC + pack (pack warps stream PCM out while the frames are still being decoded),
+// followed by the fix-up of frames whose decode failed after part of their PCM had been written
+cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
+cudaError_t launch_fix(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_k3(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);
 
 // position-weighted checksum of device bytes (see alacgpu_pcm_checksum)

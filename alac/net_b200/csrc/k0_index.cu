@@ -54,7 +54,7 @@ parse_one(const uint32_t f, const uint8_t *__restrict__ arena, const FrameRef *_
     d.status = FS_OK; d.rss = 0; d.mix_shift = 0; d.mix_weight = 0;
     d.order[0] = d.order[1] = 0; d.quant[0] = d.quant[1] = 0; d.rice_mod[0] = d.rice_mod[1] = 0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) d.pad[k] = 0;
+    for (int k = 0; k < 5; k++) d.pad[k] = 0;
     FrameCoefs fc;
 #pragma unroll
     for (int k = 0; k < 32; k++) { fc.c[0][k] = 0; fc.c[1][k] = 0; }
@@ -114,6 +114,7 @@ parse_one(const uint32_t f, const uint8_t *__restrict__ arena, const FrameRef *_
     }
     d.n = (uint16_t)n;
     d.status = status;
+    d.status0 = status;
     desc[f] = d;
     coefs[f] = fc;
     return d.out_len;

@@ -22,8 +22,11 @@
 // LOWER block indices and are therefore resident or finished by the time it
 // runs (the same assumption decoupled look-back scans rest on); the wait is
 // bounded anyway and flags ALACGPU_FRAME_INTERNAL instead of hanging.
+#include <cstdlib>
+
 #include "k1_entropy.cuh"
 #include "k2_lpc.cuh"
+#include "k3_pack.cuh"
 
 namespace alacgpu {
 
@@ -44,7 +47,7 @@ k2_lpc(const ChunkArgs a)
 
 static_assert(kK1Threads == kK2Threads, "the fused kernel uses one block size for both roles");
 
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, 3)
 k12_entropy_lpc(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks)
 {
     __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // 32 KB: bit rings, or 16 KB of LPC history
@@ -54,6 +57,92 @@ k12_entropy_lpc(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblock
         const uint32_t warp = ((blockIdx.x - n_eblocks) * kK2Threads + threadIdx.x) >> 5;
         lpc_role<true>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
     }
+}
+
+// ---- pack role of the fully fused launch ---------------------------------------------------------
+// A few persistent blocks at the END of the grid (an LPC or entropy warp must not turn into a pack
+// worker when it retires: it would then wait, without ever leaving the SM, on producers whose blocks
+// may not be resident yet -- measured as a deadlock broken only by the bounded wait).  Their number
+// follows the amount of PCM (launch_k123): spinning pack blocks hold SM slots, and too many of them
+// starve the producers of the other chunks in flight (148 per chunk: e2e 11 -> 26 ms).
+// A task = 256 consecutive sample-frames (one warp, 8 per lane)
+constexpr uint32_t kPackGroup = 32 * kK3PerThread;        // sample-frames per task
+
+__device__ __forceinline__ void pack_role(const ChunkArgs &a, uint8_t *stage /* 1536 B of shared memory per warp */)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t groups = (a.max_sf + kPackGroup - 1) / kPackGroup;
+    const uint32_t total = groups * a.n;
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(a.pack_next, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= total) break;
+        const uint32_t g = task / a.n, slot = task - g * a.n;
+        const FrameDesc d = a.desc[a.f0 + slot];
+        const uint32_t first = g * kPackGroup;
+        // wait for the producers (lane c polls channel c)
+        if (d.status0 == FS_OK && !(d.flags & FF_ESCAPE) && first < d.n) {
+            const uint32_t need = min((uint32_t)d.n, first + kPackGroup);
+            const bool mine = lane < ((d.flags & FF_STEREO) ? 2 : 1);
+            const uint32_t sid = slot * 2u + (uint32_t)(lane & 1);
+            const uint32_t *word = (mine && a.lpc_flag[sid]) ? a.lpc_done + sid : a.progress + sid;
+            uint32_t avail = 0;
+            bool stalled = false;
+            wait_avail(word, need, avail, mine, stalled);
+            if (__any_sync(0xffffffffu, stalled) && lane == 0) a.desc[a.f0 + slot].status = FS_INTERNAL;
+        }
+        uint32_t w[12], nbytes = 0, cnt = 0;
+        uint8_t *dst = nullptr;
+        const bool have = pack_group(a, slot, first + (uint32_t)lane * kK3PerThread, w, nbytes, cnt, dst);
+        // whole warp, whole groups, 16-byte aligned row: coalesced rows through shared memory
+        const uint8_t *dst0 = reinterpret_cast<const uint8_t *>(__shfl_sync(0xffffffffu, (unsigned long long)dst, 0));
+        const bool full = have && cnt == kK3PerThread;
+        if (__all_sync(0xffffffffu, full) && ((uintptr_t)dst0 & 15u) == 0) {
+            const uint32_t words = nbytes >> 2;                       // 4, 6, 8 or 12 per lane
+            uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
+#pragma unroll
+            for (int j = 0; j < 12; j++)
+                if ((uint32_t)j < words) sw[(uint32_t)lane * words + j] = w[j];
+            __syncwarp();
+            const uint32_t row_bytes = nbytes * 32u;
+            uint8_t *out = const_cast<uint8_t *>(dst0);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const uint32_t o = (uint32_t)r * 512u + (uint32_t)lane * 16u;
+                if (o < row_bytes) *reinterpret_cast<uint4 *>(out + o) = *reinterpret_cast<const uint4 *>(stage + o);
+            }
+            __syncwarp();
+        } else if (have) {
+            store_group(dst, w, nbytes, cnt);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kK1Threads, 3)
+k123_decode(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks, const uint32_t n_lblocks)
+{
+    __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // bit rings / LPC history / pack staging
+    if (blockIdx.x < n_eblocks) {
+        entropy_block<true>(a, lanes_log2, blockIdx.x, smem);
+    } else if (blockIdx.x < n_eblocks + n_lblocks) {
+        const uint32_t warp = ((blockIdx.x - n_eblocks) * kK2Threads + threadIdx.x) >> 5;
+        lpc_role<true>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
+    } else {
+        pack_role(a, smem + (threadIdx.x >> 5) * 2048);
+    }
+}
+
+// Frames the entropy stage gave up on AFTER the pack warps had already written part of their PCM
+// (status0 OK, status not): the contract is zero PCM of the nominal size.
+__global__ void __launch_bounds__(128)
+k3_fix_failed(const ChunkArgs a)
+{
+    const uint32_t slot = blockIdx.x;
+    const FrameDesc d = a.desc[a.f0 + slot];
+    if (d.status == FS_OK || d.status0 != FS_OK) return;
+    uint8_t *dst = a.pcm + (a.frame_off[a.f0 + slot] - a.pcm_base);
+    for (uint32_t i = threadIdx.x; i < d.out_len; i += 128) dst[i] = 0;
 }
 
 static int lanes_log2_of(int lanes_per_warp)
@@ -77,7 +166,7 @@ cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, u
 cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    k0s_order_sort<<<1, kSortThreads, 0, st>>>(a.desc + a.f0, a.n, a.perm, a.perm_count);
+    k0s_order_sort<<<1, kSortThreads, 0, st>>>(a.desc + a.f0, a.n, a.perm, a.perm_count, a.lpc_flag);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -99,6 +188,31 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     const uint32_t eblocks = (ewarps + 3) / 4;
     const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;
     k12_entropy_lpc<<<eblocks + (lwarps + 3) / 4, kK1Threads, 0, st>>>(a, lg, eblocks);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches)
+{
+    if (a.n == 0) return cudaSuccess;
+    const int lg = lanes_log2_of(lanes_per_warp);
+    const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
+    const uint32_t eblocks = (ewarps + 3) / 4;
+    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;
+    const uint32_t lblocks = (lwarps + 3) / 4;
+    // pack blocks: one per ~2400 tasks (a task is ~2.5 us of one warp, the decode stages leave ~2.5 ms)
+    const uint32_t tasks = ((a.max_sf + kPackGroup - 1) / kPackGroup) * a.n;
+    static const uint32_t div = getenv("ALACGPU_PACK_DIV") ? (uint32_t)atoi(getenv("ALACGPU_PACK_DIV")) : 2400u;
+    const uint32_t pblocks = tasks / div + 2u < 148u ? tasks / div + 2u : 148u;
+    k123_decode<<<eblocks + lblocks + pblocks, kK1Threads, 0, st>>>(a, lg, eblocks, lblocks);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fix(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
+{
+    if (a.n == 0) return cudaSuccess;
+    k3_fix_failed<<<a.n, 128, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

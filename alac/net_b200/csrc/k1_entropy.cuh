@@ -282,6 +282,7 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
             if (work && c < ech) publish(prog, kStreamDone);
         }
     }
+    cp_async_wait<0>();            // nothing may land in the ring after this block's shared memory is reused
     if (work) {
         // The cursor is monotone: it ended past the frame iff some symbol did.
         if (d.data_bit + br.consumed() > ref.len * 8u) status = FS_OVERRUN;

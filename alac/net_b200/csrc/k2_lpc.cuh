@@ -49,7 +49,7 @@ __device__ __forceinline__ int lpc_key(const FrameDesc &d, int ch)
 
 __global__ void __launch_bounds__(kSortThreads)
 k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *__restrict__ perm,
-               uint32_t *__restrict__ perm_count)
+               uint32_t *__restrict__ perm_count, uint8_t *__restrict__ lpc_flag)
 {
     __shared__ uint32_t hist[32], cursor[32];
     if (threadIdx.x < 32) hist[threadIdx.x] = 0;
@@ -70,6 +70,7 @@ k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *
     for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
         const int key = lpc_key(desc[s >> 1], (int)(s & 1u));
         if (key >= 0) perm[atomicAdd(&cursor[key], 1u)] = s;
+        lpc_flag[s] = key >= 0 ? 1 : 0;
     }
 }
 
@@ -109,6 +110,10 @@ constexpr int kK2Threads = 128;    // four LPC warps per block; blocks are issue
 //   row    : the lane's row of the plane (16-byte aligned), n samples (0 if inactive)
 //   nmax   : warp maximum of n
 //   ord    : 1..30 general, 31 delta mode (AlacFile.cs:268-282); inactive lanes pass 31
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 {
     uint32_t v;
@@ -143,7 +148,7 @@ template <int M, bool kPoll>
 __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int ord,
                                       const int q, const int16_t *__restrict__ coef16, const bool active,
                                       int32_t *hist /* this lane's column of a [32][32] shared ring */,
-                                      const uint32_t *prog)
+                                      const uint32_t *prog, uint32_t *done)
 {
     const bool delta = ord == 31;
     const int ordm = delta ? 0 : ord;              // taps this lane really has
@@ -222,8 +227,16 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
             o0 = u == 0 ? o : o0; o1 = u == 1 ? o : o1; o2 = u == 2 ? o : o2; o3 = u == 3 ? o : o3;
         }
         if (active && b < nblk) row4[b] = make_int4(o0, o1, o2, o3);
+        if (kPoll && (b & 7) == 7) {                 // hand-off to the pack warps, every 32 samples
+            __threadfence();
+            if (active && b < nblk) st_relaxed(done, (uint32_t)(b + 1) * 4u);
+        }
         cur = nx1;
         nx1 = nx2;
+    }
+    if (kPoll) {
+        __threadfence();
+        if (active) st_relaxed(done, 0xFFFFFFFFu);
     }
     return stalled;
 }
@@ -242,6 +255,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
     const int16_t *coef16 = nullptr;
     int32_t *row = nullptr;
     const uint32_t *prog = nullptr;
+    uint32_t *done = nullptr;
     uint64_t f = 0;
     if (active) {
         const uint32_t sid = a.perm[idx];
@@ -252,6 +266,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
         coef16 = a.coefs[f].c[ch];
         row = a.planes + (uint64_t)sid * a.ns;
         prog = a.progress + sid;
+        done = a.lpc_done + sid;
     }
     // taps needed by this warp: delta mode (31) needs none
     const int need = active ? (ord == 31 ? 1 : ord) : 0;
@@ -259,7 +274,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     int32_t *hist = hist_warp + lane;
     bool stalled;
-#define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll>(row, n, nmax, rss, ord, q, coef16, active, hist, prog)
+#define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll>(row, n, nmax, rss, ord, q, coef16, active, hist, prog, done)
     if (maxo <= 2) ALACGPU_LPC(2);
     else if (maxo <= 4) ALACGPU_LPC(4);
     else if (maxo <= 6) ALACGPU_LPC(6);

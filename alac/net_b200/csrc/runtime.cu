@@ -89,7 +89,8 @@ struct Slot {
     cudaStream_t st = nullptr;
     DevBuf<int32_t> planes;
     DevBuf<uint32_t> perm;        // K2 work list (2 entries per frame) + 1 count word at the end
-    DevBuf<uint32_t> progress;    // fused launch: per-stream hand-off words (2 per frame)
+    DevBuf<uint32_t> progress;    // fused launch: [0,2cf) entropy->LPC words, [2cf,4cf) LPC->pack words, 4 words of
+                                  // pack task counter, then 2cf bytes of LPC work-list flags (cf = chunk frames)
 };
 
 struct Device {
@@ -118,7 +119,8 @@ struct Device {
     uint32_t chunk_frames = 0;
     std::vector<cudaEvent_t> events;
     bool resident = false;            // arena bytes + K0 results are on the device
-    bool decoded = false;
+    bool decoded = false;             // kernels ran: per-frame status is valid
+    bool pcm_resident = false;        // ... and the PCM is in `pcm` (not after a zero-copy decode)
 };
 
 }  // namespace
@@ -224,7 +226,7 @@ void invalidate(alacgpu_ctx *ctx)
     ctx->planned = false;
     ctx->have_status = false;
     ctx->win_lo = ctx->win_hi = 0;
-    for (Device &d : ctx->devs) { d.resident = false; d.decoded = false; d.chunk_frames = 0; d.chunks.clear(); }
+    for (Device &d : ctx->devs) { d.resident = false; d.decoded = false; d.pcm_resident = false; d.chunk_frames = 0; d.chunks.clear(); }
 }
 
 // Partition + per-device frame index.  Pure host work plus allocations and the small table
@@ -252,7 +254,7 @@ int32_t build_plan(alacgpu_ctx *ctx)
         Device &d = ctx->devs[g];
         d.f_lo = cut[g];
         d.f_hi = cut[g + 1];
-        d.resident = d.decoded = false;
+        d.resident = d.decoded = d.pcm_resident = false;
         d.chunks.clear();
         d.chunk_frames = 0;
         const uint64_t n_local = d.f_hi - d.f_lo;
@@ -389,14 +391,18 @@ constexpr size_t kEvBase = 4;       // [0] pipeline start, [1] pipeline end, [2]
 
 // Issue one chunk's kernels on its slot stream.
 int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool with_k0, bool with_decode,
-                    size_t ev, uint32_t *launches)
+                    size_t ev, uint32_t *launches, uint8_t *pcm_override, bool streaming)
 {
     ChunkArgs ca{};
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
     ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
     ca.perm = s.perm.p; ca.perm_count = s.perm.p + 2u * (size_t)d.chunk_frames;
+    const size_t cf2 = 2u * (size_t)d.chunk_frames;
     ca.progress = s.progress.p;
+    ca.lpc_done = s.progress.p + cf2;
+    ca.pack_next = s.progress.p + 2u * cf2;
+    ca.lpc_flag = reinterpret_cast<uint8_t *>(s.progress.p + 2u * cf2 + 4u);
     CU(cudaEventRecord(get_event(d, ev), s.st));
     if (with_k0) {
         K0Args ka{};
@@ -406,20 +412,28 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
         CU(launch_k0(ka, s.st, launches));
     }
     CU(cudaEventRecord(get_event(d, ev + 1), s.st));
-    const bool fused = !(ctx->opts.flags & ALACGPU_FLAG_NO_FUSION);
+    // fusion level: 2 = entropy + LPC + pack in one launch, 1 = entropy + LPC with K3 apart, 0 = three
+    // kernels.  Default: 2 when the inputs are resident (one launch does everything, and PCM can
+    // stream straight into a page-locked destination while the batch decodes: 8.4 vs 10.5 ms for
+    // configs[1]); 1 when chunks are being streamed in from the host (measured: the pack blocks'
+    // SM slots are better spent on the next chunks' producers, 11.7 vs 12.1 ms end to end).
+    int fused = (ctx->opts.flags & ALACGPU_FLAG_NO_FUSION) ? 0 : (ctx->opts.flags & ALACGPU_FLAG_NO_PACK_FUSION) ? 1 : 2;
+    if (fused == 2 && streaming) fused = 1;
+    if (pcm_override) { ca.pcm = pcm_override; ca.pcm_base = 0; }      // PCM straight into host-mapped memory
     if (with_decode) {
         CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
-        if (fused) {
-            CU(cudaMemsetAsync(s.progress.p, 0, (size_t)c.n * 2u * sizeof(uint32_t), s.st));
-            CU(launch_k12(ca, lanes_for(ctx), s.st, launches));
-        } else {
-            CU(launch_k1(ca, lanes_for(ctx), s.st, launches));
-        }
+        if (fused) CU(cudaMemsetAsync(s.progress.p, 0, (2u * cf2 + 4u) * sizeof(uint32_t), s.st));
+        if (fused == 2) CU(launch_k123(ca, lanes_for(ctx), s.st, launches));
+        else if (fused == 1) CU(launch_k12(ca, lanes_for(ctx), s.st, launches));
+        else CU(launch_k1(ca, lanes_for(ctx), s.st, launches));
     }
     CU(cudaEventRecord(get_event(d, ev + 2), s.st));
-    if (with_decode && !fused) CU(launch_k2(ca, s.st, launches));
+    if (with_decode && fused == 0) CU(launch_k2(ca, s.st, launches));
     CU(cudaEventRecord(get_event(d, ev + 3), s.st));
-    if (with_decode) CU(launch_k3(ca, s.st, launches));
+    if (with_decode) {
+        if (fused == 2) CU(launch_fix(ca, s.st, launches));
+        else CU(launch_k3(ca, s.st, launches));
+    }
     CU(cudaEventRecord(get_event(d, ev + 4), s.st));
     return ALACGPU_OK;
 }
@@ -430,6 +444,25 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
 {
     const int n_dev = (int)ctx->devs.size();
     uint32_t launches = 0, chunks_total = 0;
+    // Zero-copy output: when the caller's buffer is page-locked and mapped (alacgpu_host_alloc, or any
+    // cudaHostAlloc / cudaHostRegister'ed range) and the pack stage is fused, the pack warps write the
+    // PCM straight into it over PCIe while the frames are still being decoded; there is no device PCM
+    // copy and no D2H stage.
+    uint8_t *zc = nullptr;
+    if (pcm_dst && decode && !stage && !(ctx->opts.flags & (ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_PACK_FUSION | ALACGPU_FLAG_NO_ZERO_COPY))) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, pcm_dst) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            zc = static_cast<uint8_t *>(at.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    if (zc) {                      // alignment gaps between tracks are zero bytes in the layout
+        uint64_t end = 0;
+        for (const HostTrack &ht : ctx->tracks) {
+            if (ht.pcm_off > end) memset(pcm_dst + end, 0, ht.pcm_off - end);
+            end = ht.pcm_off + ht.pcm_len;
+        }
+    }
     for (int g = 0; g < n_dev; g++) {
         Device &d = ctx->devs[g];
         const uint64_t n_local = d.f_hi - d.f_lo;
@@ -450,12 +483,12 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
             for (int s = 0; s < slots_used; s++) {
                 CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
                 CU(d.slots[s].perm.reserve((size_t)cf * 2u + 4u));
-                CU(d.slots[s].progress.reserve((size_t)cf * 2u + 4u));
+                CU(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
             }
         get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
         CU(cudaEventRecord(d.events[0], d.slots[0].st));
         for (int s = 1; s < slots_used; s++) CU(cudaStreamWaitEvent(d.slots[s].st, d.events[0], 0));
-        if (pcm_dst) {
+        if (pcm_dst && !zc) {
             CU(cudaStreamWaitEvent(d.st_d2h, d.events[0], 0));
             CU(cudaEventRecord(d.events[2], d.st_d2h));
         }
@@ -470,9 +503,9 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
                 CU(cudaEventRecord(d.events[ev + 5], d.st_h2d));
                 CU(cudaStreamWaitEvent(s.st, d.events[ev + 5], 0));
             }
-            int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &launches);
+            int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &launches, zc, stage);
             if (r) return r;
-            if (pcm_dst && decode && c.pcm_hi > c.pcm_lo) {
+            if (pcm_dst && !zc && decode && c.pcm_hi > c.pcm_lo) {
                 CU(cudaStreamWaitEvent(d.st_d2h, d.events[ev + 4], 0));
                 CU(cudaMemcpyAsync(pcm_dst + c.pcm_lo, d.pcm.p + (c.pcm_lo - d.pcm_lo), c.pcm_hi - c.pcm_lo,
                                    cudaMemcpyDeviceToHost, d.st_d2h));
@@ -483,7 +516,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         for (size_t ci = n_chunks > (size_t)kSlots ? n_chunks - kSlots : 0; ci < n_chunks; ci++)
             if (ci % kSlots != 0) CU(cudaStreamWaitEvent(d.slots[0].st, d.events[kEvBase + ci * kEvPerChunk + 4], 0));
         CU(cudaEventRecord(d.events[1], d.slots[0].st));
-        if (pcm_dst) CU(cudaEventRecord(d.events[3], d.st_d2h));
+        if (pcm_dst && !zc) CU(cudaEventRecord(d.events[3], d.st_d2h));
     }
     // ---- wait + timings --------------------------------------------------------
     float k0 = 0, k1 = 0, k2 = 0, k3 = 0, kall = 0, d2h = 0, h2d = 0;
@@ -492,7 +525,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (d.f_hi == d.f_lo) continue;
         CU(cudaSetDevice(d.id));
         CU(cudaStreamSynchronize(d.slots[0].st));
-        if (pcm_dst) CU(cudaStreamSynchronize(d.st_d2h));
+        if (pcm_dst && !zc) CU(cudaStreamSynchronize(d.st_d2h));
         if (stage) CU(cudaStreamSynchronize(d.st_h2d));
         float s0 = 0, s1 = 0, s2 = 0, s3 = 0, ms = 0;
         for (size_t ci = 0; ci < d.chunks.size(); ci++) {
@@ -505,13 +538,13 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         cudaEventElapsedTime(&ms, d.events[0], d.events[1]);
         k0 = std::max(k0, s0); k1 = std::max(k1, s1); k2 = std::max(k2, s2); k3 = std::max(k3, s3);
         kall = std::max(kall, ms);
-        if (pcm_dst) { cudaEventElapsedTime(&ms, d.events[2], d.events[3]); d2h = std::max(d2h, ms); }
+        if (pcm_dst && !zc) { cudaEventElapsedTime(&ms, d.events[2], d.events[3]); d2h = std::max(d2h, ms); }
         if (stage) {
             cudaEventElapsedTime(&ms, d.events[0], d.events[kEvBase + (d.chunks.size() - 1) * kEvPerChunk + 5]);
             h2d = std::max(h2d, ms);
         }
         if (stage || index) d.resident = true;
-        if (decode) d.decoded = true;
+        if (decode) { d.decoded = true; d.pcm_resident = !zc; }     // zero-copy output leaves no PCM in HBM
         if (index) {
             uint32_t mism = 0;
             CU(cudaMemcpy(&mism, d.scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -523,7 +556,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
     if (decode) { tm.entropy_ms = k1; tm.lpc_ms = k2; tm.stereo_ms = k3; }
     tm.kernels_ms = kall;
     if (stage) tm.h2d_ms = h2d;
-    if (pcm_dst) tm.d2h_ms = d2h;
+    if (pcm_dst) tm.d2h_ms = zc ? 0.f : d2h;
     tm.chunks = chunks_total;
     if (launches_out) *launches_out = launches;
     ctx->have_status = false;
@@ -553,6 +586,13 @@ bool all_decoded(alacgpu_ctx *ctx)
 {
     if (!ctx->planned) return false;
     for (Device &d : ctx->devs) if (d.f_hi > d.f_lo && !d.decoded) return false;
+    return true;
+}
+
+bool all_pcm_resident(alacgpu_ctx *ctx)
+{
+    if (!ctx->planned) return false;
+    for (Device &d : ctx->devs) if (d.f_hi > d.f_lo && !d.pcm_resident) return false;
     return true;
 }
 
@@ -841,7 +881,7 @@ int32_t alacgpu_read_frame(alacgpu_ctx *ctx, int32_t track, uint32_t frame_idx, 
     *bytes_out = 0;
     const HostTrack &ht = ctx->tracks[track];
     if (frame_idx >= ht.n_frames) return ALACGPU_OK;          // AlacContext.cs:182-186: return 0
-    if (!all_decoded(ctx)) {
+    if (!all_pcm_resident(ctx)) {
         r = alacgpu_decode_all(ctx, nullptr, 0, nullptr, nullptr, nullptr);
         if (r) return r;
     }
@@ -928,7 +968,7 @@ int32_t alacgpu_device_pcm(alacgpu_ctx *ctx, int32_t dev_slot, void **dptr, uint
 {
     if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return ALACGPU_ERR_INVALID_ARG;
     Device &d = ctx->devs[dev_slot];
-    if (!d.decoded && d.f_hi > d.f_lo) return fail(ctx, ALACGPU_ERR_STATE, "no decoded PCM on this device");
+    if (!d.pcm_resident && d.f_hi > d.f_lo) return fail(ctx, ALACGPU_ERR_STATE, "no decoded PCM on this device");
     if (dptr) *dptr = d.pcm.p;
     if (shard_off) *shard_off = d.pcm_lo;
     if (shard_len) *shard_len = d.pcm_hi - d.pcm_lo;
@@ -941,7 +981,7 @@ int32_t alacgpu_pcm_checksum(alacgpu_ctx *ctx, uint64_t off, uint64_t len, uint6
     uint64_t total = 0;
     for (Device &d : ctx->devs) {
         if (d.f_hi == d.f_lo) continue;
-        if (!d.decoded) return fail(ctx, ALACGPU_ERR_STATE, "no decoded PCM on this device");
+        if (!d.pcm_resident) return fail(ctx, ALACGPU_ERR_STATE, "no decoded PCM on this device (decode with pcm_dst == NULL first)");
         // this shard's bytes inside [off, off+len); shards start on 256-byte boundaries of the
         // global layout except where a track is split between devices (then on a frame boundary)
         uint64_t lo = std::max(off, d.pcm_first), hi = std::min(off + len, d.pcm_hi);

@@ -207,7 +207,7 @@ def batch_leg(args, local):
             pb.array[:] = np.frombuffer(t.mdat, dtype=np.uint8)
             pinned[id(t)] = pb
     samples = sum(t.n_samples for t in tracks)
-    with BatchDecoder(devices=[local], flags=(2 if args.no_fusion else 0)) as dec:
+    with BatchDecoder(devices=[local], flags=args.flags | (2 if args.no_fusion else 0)) as dec:
         for t in tracks:
             dec.add_track(t.cfg, pinned[id(t)], t.stsz)
         dec.prepare()
@@ -273,7 +273,7 @@ def run_ours(args):
         pinned.append(pb)
 
     dec = BatchDecoder(devices=[local], chunk_frames=args.chunk_frames, entropy_lanes=args.entropy_lanes,
-                       flags=(2 if args.no_fusion else 0))
+                       flags=args.flags | (2 if args.no_fusion else 0))
     for t, pb in zip(tracks, pinned):
         dec.add_track(t.cfg, pb, t.stsz)
     total = dec.prepare()              # stage the mdat in HBM + header pre-pass: inputs resident
@@ -284,6 +284,7 @@ def run_ours(args):
     ok = bool((status == 0).all())
     for t, o_, l_ in zip(tracks, off, ln):
         ok = ok and out[int(o_):int(o_ + l_)].tobytes() == t.pcm
+    dec.decode_all(False, want_status=False)      # device-resident copy for the on-device checksum
     dev_sum = dec.checksum()
     ok = ok and dev_sum == host_checksum(out[:total])
     if not ok:
@@ -344,8 +345,10 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         stage = {k: acc[k] / args.steps for k in acc}
         b_alg = comp_bytes + pcm_bytes
-        fused = not args.no_fusion
-        names = {"entropy_ms": "k12_entropy_lpc (fused entropy + LPC)" if fused else "k1_entropy",
+        fused = not (args.no_fusion or (args.flags & 2))
+        pack_fused = fused and not (args.flags & 4)
+        names = {"entropy_ms": ("k123_decode (fused entropy + LPC + pack)" if pack_fused else
+                                "k12_entropy_lpc (fused entropy + LPC)") if fused else "k1_entropy",
                  "lpc_ms": "k2_lpc", "stereo_ms": "k3_stereo_pack"}
         dom = max(("entropy_ms", "lpc_ms", "stereo_ms"), key=lambda k: stage[k])
         path_ms = stage["index_ms"] + stage["kernels_ms"]
@@ -381,7 +384,8 @@ def run_ours(args):
             "e2e": {"value": samples_all / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": int(comp_bytes + 4 * n_frames), "d2h_bytes_per_step": int(pcm_bytes),
                     "ms_per_step": e2e_ms_max, "steps": args.e2e_steps,
-                    "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"]},
+                    "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"], "pipeline_ms": tm_e2e["kernels_ms"],
+                    "api_ms": tm_e2e["total_ms"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": names[dom],
@@ -420,6 +424,7 @@ def main():
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--entropy-lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="ALACGPU_FLAG_* bits: 2 no fusion, 4 no pack fusion, 8 no zero-copy output")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--batch-tracks", type=int, default=64, help="tracks of the configs[3]-shaped throughput leg (0 = skip)")
     ap.add_argument("--no-fusion", action="store_true", help="entropy and LPC as two kernels (A/B against the fused launch)")

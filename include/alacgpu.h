@@ -95,7 +95,9 @@ typedef struct alacgpu_ctx alacgpu_ctx;
 
 /* ---- options ------------------------------------------------------------- */
 #define ALACGPU_FLAG_KEEP_DEVICE_PCM 0x1u  /* keep decoded PCM resident in HBM after decode_all */
-#define ALACGPU_FLAG_NO_FUSION 0x2u        /* run entropy and LPC as two kernels instead of the fused, overlapped launch */
+#define ALACGPU_FLAG_NO_FUSION 0x2u        /* entropy, LPC and pack as three kernels instead of the fused, overlapped launch */
+#define ALACGPU_FLAG_NO_PACK_FUSION 0x4u   /* fuse entropy + LPC only; un-mix / pack stays a separate kernel */
+#define ALACGPU_FLAG_NO_ZERO_COPY 0x8u     /* never write PCM straight into a page-locked destination; always device PCM + D2H copies */
 
 typedef struct alacgpu_opts {
     uint32_t struct_size;      /* sizeof(alacgpu_opts), for forward compatibility       */
@@ -122,9 +124,9 @@ typedef struct alacgpu_track_cfg {
  * recorded on the streams the kernels were launched on. */
 typedef struct alacgpu_timing {
     float index_ms;        /* K0 header pre-pass, summed over chunks             */
-    float entropy_ms;      /* K1, summed over chunks (fused launch: K1 and K2 together) */
+    float entropy_ms;      /* K1, summed over chunks (fused launch: every stage fused into it) */
     float lpc_ms;          /* K2 (0 when fused into the entropy launch)          */
-    float stereo_ms;       /* K3                                                 */
+    float stereo_ms;       /* K3 (fully fused launch: only the failed-frame fix-up) */
     float kernels_ms;      /* device pipeline span: first launch -> last kernel done (includes waits for H2D when streaming) */
     float h2d_ms;          /* mdat staging copies: first copy issued -> last done */
     float d2h_ms;          /* PCM copies to the caller's buffer                  */

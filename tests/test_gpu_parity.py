@@ -5,11 +5,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _decode(tracks, dst=None, **kw):
+def _decode(tracks, dst=None, resident=False, **kw):
+    """resident=False: decode_all streams the mdat in chunk by chunk (entropy + LPC fused, K3 apart);
+    resident=True: prepare() first, then ONE fully fused launch per chunk (entropy + LPC + pack)."""
     from alac.net_b200 import BatchDecoder
     with BatchDecoder(**kw) as dec:
         for t in tracks:
             dec.add_track(t.cfg, t.mdat, t.stsz)
+        if resident:
+            dec.prepare()
         pcm, off, ln, status = dec.decode_all(dst)
         timing = dec.timing()
         return [pcm[int(o):int(o + l)].tobytes() for o, l in zip(off, ln)], status, timing
@@ -34,10 +38,11 @@ def _assert_tracks_equal(tracks, got, status, oracle, check_encoder=True):
         pos += t.n_frames
 
 
+@pytest.mark.parametrize("resident", [False, True])
 @pytest.mark.parametrize("k,scale", [(1, 0.1), (2, 0.02), (3, 0.2)])
-def test_configs_small(k, scale, gen, oracle):
+def test_configs_small(k, scale, resident, gen, oracle):
     tracks = gen.make_config(k, scale=scale)
-    got, status, timing = _decode(tracks)
+    got, status, timing = _decode(tracks, resident=resident)
     _assert_tracks_equal(tracks, got, status, oracle)
     assert timing["kernel_launches"] > 0
 
@@ -59,8 +64,9 @@ def test_config3_full_size_divergence(gen, oracle):
 def test_config4_and_5_shaped_batches(gen, oracle):
     """many tracks in one decode_all: 16-bit stereo batch (config 4) and the 16/24 mono/stereo mix (config 5)"""
     tracks = gen.make_config(4, scale=0.004, n_tracks=24) + gen.make_config(5, scale=0.004, n_tracks=20)
-    got, status, _ = _decode(tracks)
-    _assert_tracks_equal(tracks, got, status, oracle)
+    for resident in (False, True):
+        got, status, _ = _decode(tracks, resident=resident)
+        _assert_tracks_equal(tracks, got, status, oracle)
 
 
 @pytest.mark.parametrize("lanes", [8, 16, 32])
@@ -71,15 +77,44 @@ def test_chunking_and_lane_options_do_not_change_bytes(lanes, chunk, gen, oracle
     _assert_tracks_equal(tracks, got, status, oracle)
 
 
-@pytest.mark.parametrize("flags", [0, 2])
+@pytest.mark.parametrize("flags", [0, 2, 4])
 def test_fused_and_two_kernel_paths_agree(flags, gen, oracle):
     """ALACGPU_FLAG_NO_FUSION (2): entropy and LPC as two launches; default: one fused launch in which
     the LPC warps consume residuals while the entropy lanes are still decoding"""
     tracks = gen.make_config(2, scale=0.02) + gen.make_config(1, scale=0.1) + gen.make_config(3, scale=0.1)
+    got, status, tm = _decode(tracks, flags=flags, resident=True)
+    _assert_tracks_equal(tracks, got, status, oracle)
+    # inputs resident: K123 + fix (default) / K12 + K3 (4) / K1 + K2 + K3 (2); K0 + sort ran in prepare / per chunk
     got, status, tm = _decode(tracks, flags=flags)
     _assert_tracks_equal(tracks, got, status, oracle)
-    # K0 + sort + K12 + K3 per chunk when fused; K0 + sort + K1 + K2 + K3 otherwise
+    # per chunk (inputs streamed in): K0 + sort + K12 + K3 (default and 4) / K0 + sort + K1 + K2 + K3 (2)
     assert tm["kernel_launches"] == tm["chunks"] * (5 if flags == 2 else 4)
+
+
+def test_zero_copy_output_into_pinned_memory(gen, oracle):
+    """page-locked destination: the pack warps of the fused launch write the PCM straight into it
+    (no device PCM, no D2H stage); pageable destination and ALACGPU_FLAG_NO_ZERO_COPY take the copy path"""
+    from alac.net_b200 import BatchDecoder, PinnedBuffer
+    tracks = gen.make_config(2, scale=0.02) + gen.make_config(3, scale=0.1) + gen.make_config(1, scale=0.05)
+    refs = [_oracle(oracle, t)[0] for t in tracks]
+    for flags in (0, 8):
+        with BatchDecoder(devices=[0], flags=flags) as dec:
+            for t in tracks:
+                dec.add_track(t.cfg, t.mdat, t.stsz)
+            dec.prepare()                            # inputs resident: the fully fused launch + zero-copy output
+            buf = PinnedBuffer(dec.total_pcm_bytes())
+            buf.array[:] = 0xAB                      # alignment gaps must come back as zeros
+            out, off, ln, status = dec.decode_all(buf)
+            tm = dec.timing()
+            assert (status == 0).all()
+            for r, o, l in zip(refs, off, ln):
+                assert out[int(o):int(o + l)].tobytes() == r
+            for (o, l), nxt in zip(zip(off, ln), list(off[1:]) + [dec.total_pcm_bytes()]):
+                assert not out[int(o + l):int(nxt)].any()
+            assert (tm["d2h_ms"] == 0.0) == (flags == 0)
+            # the per-frame pull still works afterwards (it decodes device-resident on demand)
+            assert dec.read_frame(0, 1) == refs[0][24576:2 * 24576]
+            buf.free()
 
 
 def test_resident_path_equals_streaming_path(gen, oracle):
@@ -151,9 +186,10 @@ def test_truncated_and_malformed_frames_follow_the_oracle_policy(gen, oracle):
         md[offs[f]] = (md[offs[f]] & 0x1F) | (int(rng.integers(2, 8)) << 5)
     tc = gen.Track(t.cfg, bytes(md), t.stsz, t.frame_samples, b"")
     tracks = [ta, tb, tc]
-    got, status, _ = _decode(tracks)
-    _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
-    assert (status != 0).any()
+    for resident in (False, True):
+        got, status, _ = _decode(tracks, resident=resident)
+        _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
+        assert (status != 0).any()
 
 
 def test_kmodifier_and_history_cookie_variants(gen, oracle):
@@ -281,7 +317,7 @@ def test_random_payload_fuzz_matches_oracle(seed, gen, oracle):
         cfg = gen.TrackCfg(ss, cch, max_n, hm, ih, kmod, 44100)
         stsz = np.array([len(f) for f in frames], dtype=np.uint32)
         tracks.append(gen.Track(cfg, b"".join(frames), stsz, np.zeros(len(frames), np.int32), b""))
-    for flags in (0, 2):
-        got, status, _ = _decode(tracks, flags=flags)
+    for flags, resident in ((0, True), (0, False), (2, False), (4, True)):
+        got, status, _ = _decode(tracks, flags=flags, resident=resident)
         _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
         assert (status == 0).any() and (status != 0).any()
