@@ -42,12 +42,12 @@ k2_lpc(const ChunkArgs a)
 {
     __shared__ int32_t hist_smem[32 * kK2Threads];
     const uint32_t warp = (blockIdx.x * kK2Threads + threadIdx.x) >> 5;
-    lpc_role<false>(a, warp, hist_smem + (threadIdx.x >> 5) * 1024);
+    lpc_role<false, false>(a, warp, hist_smem + (threadIdx.x >> 5) * 1024);
 }
 
 static_assert(kK1Threads == kK2Threads, "the fused kernel uses one block size for both roles");
 
-__global__ void __launch_bounds__(kK1Threads, 3)
+__global__ void __launch_bounds__(kK1Threads)
 k12_entropy_lpc(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks)
 {
     __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // 32 KB: bit rings, or 16 KB of LPC history
@@ -55,7 +55,7 @@ k12_entropy_lpc(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblock
         entropy_block<true>(a, lanes_log2, blockIdx.x, smem);
     } else {
         const uint32_t warp = ((blockIdx.x - n_eblocks) * kK2Threads + threadIdx.x) >> 5;
-        lpc_role<true>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
+        lpc_role<true, false>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
     }
 }
 
@@ -119,7 +119,7 @@ __device__ __forceinline__ void pack_role(const ChunkArgs &a, uint8_t *stage /* 
     }
 }
 
-__global__ void __launch_bounds__(kK1Threads, 3)
+__global__ void __launch_bounds__(kK1Threads)
 k123_decode(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks, const uint32_t n_lblocks)
 {
     __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // bit rings / LPC history / pack staging
@@ -127,7 +127,7 @@ k123_decode(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks, c
         entropy_block<true>(a, lanes_log2, blockIdx.x, smem);
     } else if (blockIdx.x < n_eblocks + n_lblocks) {
         const uint32_t warp = ((blockIdx.x - n_eblocks) * kK2Threads + threadIdx.x) >> 5;
-        lpc_role<true>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
+        lpc_role<true, true>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
     } else {
         pack_role(a, smem + (threadIdx.x >> 5) * 2048);
     }

@@ -144,7 +144,7 @@ __device__ __forceinline__ void wait_avail(const uint32_t *prog, const uint32_t 
     }
 }
 
-template <int M, bool kPoll>
+template <int M, bool kPoll, bool kPublish>
 __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int ord,
                                       const int q, const int16_t *__restrict__ coef16, const bool active,
                                       int32_t *hist /* this lane's column of a [32][32] shared ring */,
@@ -227,14 +227,14 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
             o0 = u == 0 ? o : o0; o1 = u == 1 ? o : o1; o2 = u == 2 ? o : o2; o3 = u == 3 ? o : o3;
         }
         if (active && b < nblk) row4[b] = make_int4(o0, o1, o2, o3);
-        if (kPoll && (b & 7) == 7) {                 // hand-off to the pack warps, every 32 samples
+        if (kPublish && (b & 7) == 7) {              // hand-off to the pack warps, every 32 samples
             __threadfence();
             if (active && b < nblk) st_relaxed(done, (uint32_t)(b + 1) * 4u);
         }
         cur = nx1;
         nx1 = nx2;
     }
-    if (kPoll) {
+    if (kPublish) {
         __threadfence();
         if (active) st_relaxed(done, 0xFFFFFFFFu);
     }
@@ -242,7 +242,7 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
 }
 
 // One LPC warp: streams perm[warp * 32 + lane].  hist: this warp's [32][32] int32 ring.
-template <bool kPoll>
+template <bool kPoll, bool kPublish>
 __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp, int32_t *hist_warp)
 {
     const int lane = threadIdx.x & 31;
@@ -274,7 +274,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     int32_t *hist = hist_warp + lane;
     bool stalled;
-#define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll>(row, n, nmax, rss, ord, q, coef16, active, hist, prog, done)
+#define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, hist, prog, done)
     if (maxo <= 2) ALACGPU_LPC(2);
     else if (maxo <= 4) ALACGPU_LPC(4);
     else if (maxo <= 6) ALACGPU_LPC(6);

@@ -42,6 +42,7 @@ constexpr uint64_t kTrackAlign = 256;     // PCM start alignment of each track i
 constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
 constexpr int kSlots = 16;
+constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -418,7 +419,9 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     // configs[1]); 1 when chunks are being streamed in from the host (measured: the pack blocks'
     // SM slots are better spent on the next chunks' producers, 11.7 vs 12.1 ms end to end).
     int fused = (ctx->opts.flags & ALACGPU_FLAG_NO_FUSION) ? 0 : (ctx->opts.flags & ALACGPU_FLAG_NO_PACK_FUSION) ? 1 : 2;
-    if (fused == 2 && streaming) fused = 1;
+    // ... and 1 again for chunks that fill the machine (> ~20k frames: issue-bound, no idle SMs for
+    // pack blocks to use; measured 59 vs 72 Gsamples/s on a 174k-frame batch).
+    if (fused == 2 && (streaming || c.n > kFullFusionMaxFrames)) fused = 1;
     if (pcm_override) { ca.pcm = pcm_override; ca.pcm_base = 0; }      // PCM straight into host-mapped memory
     if (with_decode) {
         CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
@@ -448,8 +451,22 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
     // cudaHostAlloc / cudaHostRegister'ed range) and the pack stage is fused, the pack warps write the
     // PCM straight into it over PCIe while the frames are still being decoded; there is no device PCM
     // copy and no D2H stage.
+    // chunk size: as much as possible in flight at once when the bytes are already resident;
+    // ~kSlots chunks when streaming from the host so copies and kernels overlap
+    auto chunk_frames_for = [&](const Device &d) {
+        const uint64_t n_local = d.f_hi - d.f_lo;
+        uint32_t cf = ctx->opts.chunk_frames;
+        if (!cf) {
+            if (stage) cf = (uint32_t)std::max<uint64_t>(256, (n_local + kSlots - 1) / kSlots);
+            else cf = (uint32_t)std::min<uint64_t>(n_local, kMaxChunkFrames);
+        }
+        return std::min<uint32_t>((cf + 31u) & ~31u, kMaxChunkFrames);
+    };
+    bool all_fully_fused = !stage;
+    for (const Device &d : ctx->devs)
+        if (d.f_hi > d.f_lo && chunk_frames_for(d) > kFullFusionMaxFrames) all_fully_fused = false;
     uint8_t *zc = nullptr;
-    if (pcm_dst && decode && !stage && !(ctx->opts.flags & (ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_PACK_FUSION | ALACGPU_FLAG_NO_ZERO_COPY))) {
+    if (pcm_dst && decode && all_fully_fused && !(ctx->opts.flags & (ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_PACK_FUSION | ALACGPU_FLAG_NO_ZERO_COPY))) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, pcm_dst) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             zc = static_cast<uint8_t *>(at.devicePointer);
@@ -468,14 +485,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         const uint64_t n_local = d.f_hi - d.f_lo;
         if (!n_local) continue;
         CU(cudaSetDevice(d.id));
-        // chunk size: as much as possible in flight at once when the bytes are already
-        // resident; ~kSlots chunks when streaming from the host so copies and kernels overlap
-        uint32_t cf = ctx->opts.chunk_frames;
-        if (!cf) {
-            if (stage) cf = (uint32_t)std::max<uint64_t>(256, (n_local + kSlots - 1) / kSlots);
-            else cf = (uint32_t)std::min<uint64_t>(n_local, kMaxChunkFrames);
-        }
-        cf = std::min<uint32_t>((cf + 31u) & ~31u, kMaxChunkFrames);
+        const uint32_t cf = chunk_frames_for(d);
         build_chunks(ctx, d, cf);
         const size_t n_chunks = d.chunks.size();
         const int slots_used = (int)std::min<size_t>(kSlots, n_chunks);
