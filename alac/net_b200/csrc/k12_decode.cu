@@ -47,7 +47,7 @@ k2_lpc(const ChunkArgs a)
 
 static_assert(kK1Threads == kK2Threads, "the fused kernel uses one block size for both roles");
 
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, 3)
 k12_entropy_lpc(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks)
 {
     __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // 32 KB: bit rings, or 16 KB of LPC history
@@ -119,7 +119,7 @@ __device__ __forceinline__ void pack_role(const ChunkArgs &a, uint8_t *stage /* 
     }
 }
 
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, 3)
 k123_decode(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks, const uint32_t n_lblocks)
 {
     __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // bit rings / LPC history / pack staging
@@ -166,7 +166,7 @@ cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, u
 cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    k0s_order_sort<<<1, kSortThreads, 0, st>>>(a.desc + a.f0, a.n, a.perm, a.perm_count, a.lpc_flag);
+    k0s_order_sort<<<1, kSortThreads, 0, st>>>(a.desc + a.f0, a.n, a.perm, a.perm_count, a.lpc_flag, a.use_quads);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -174,7 +174,8 @@ cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    const uint32_t warps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;   // upper bound; warps past n_active exit at once
+    // upper bound; warps past the work lists exit at once
+    const uint32_t warps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
     k2_lpc<<<(warps + 3) / 4, kK2Threads, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -186,7 +187,7 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;
+    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
     k12_entropy_lpc<<<eblocks + (lwarps + 3) / 4, kK1Threads, 0, st>>>(a, lg, eblocks);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -198,7 +199,7 @@ cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st,
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP;
+    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
     const uint32_t lblocks = (lwarps + 3) / 4;
     // pack blocks: one per ~2400 tasks (a task is ~2.5 us of one warp, the decode stages leave ~2.5 ms)
     const uint32_t tasks = ((a.max_sf + kPackGroup - 1) / kPackGroup) * a.n;

@@ -47,17 +47,33 @@ __device__ __forceinline__ int lpc_key(const FrameDesc &d, int ch)
     return d.order[ch] == 31 ? 0 : d.order[ch];
 }
 
+// Streams that set the batch's critical path when the chunk is small (fewer frames than lanes): the
+// LAST channel of a frame with a high predictor order.  Its residuals only start to appear once
+// the entropy lane has finished the other channel, and its order-30 recurrence is the slowest thing
+// in the pipeline, so these streams get FOUR lanes each (lpc_warp4) instead of one.  The rest of the
+// streams have slack and stay one lane per stream.
+constexpr int kQuadMinOrder = 17;
+
+__device__ __forceinline__ bool lpc_quad(const FrameDesc &d, int ch, int key)
+{
+    const int last = (d.flags & FF_STEREO) ? 1 : 0;
+    return key >= kQuadMinOrder && ch == last;
+}
+
+// perm[0 .. n_rest): one-lane streams, heaviest first; perm[2n .. 2n + n_quad): four-lane streams,
+// heaviest first; perm_count[0] = n_rest, perm_count[1] = n_quad.
 __global__ void __launch_bounds__(kSortThreads)
 k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *__restrict__ perm,
-               uint32_t *__restrict__ perm_count, uint8_t *__restrict__ lpc_flag)
+               uint32_t *__restrict__ perm_count, uint8_t *__restrict__ lpc_flag, const int use_quads)
 {
-    __shared__ uint32_t hist[32], cursor[32];
-    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+    __shared__ uint32_t hist[64], cursor[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t n_streams = n_frames * 2u;
     for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
-        const int key = lpc_key(desc[s >> 1], (int)(s & 1u));
-        if (key >= 0) atomicAdd(&hist[key], 1u);
+        const FrameDesc d = desc[s >> 1];
+        const int key = lpc_key(d, (int)(s & 1u));
+        if (key >= 0) atomicAdd(&hist[key + ((use_quads && lpc_quad(d, (int)(s & 1u), key)) ? 32 : 0)], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -65,11 +81,15 @@ k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *
         for (int key = 30; key >= 0; --key) { cursor[key] = acc; acc += hist[key]; }
         cursor[31] = 0;
         perm_count[0] = acc;
+        acc = 0;
+        for (int key = 30; key >= 0; --key) { cursor[32 + key] = n_streams + acc; acc += hist[32 + key]; }
+        perm_count[1] = acc;
     }
     __syncthreads();
     for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
-        const int key = lpc_key(desc[s >> 1], (int)(s & 1u));
-        if (key >= 0) perm[atomicAdd(&cursor[key], 1u)] = s;
+        const FrameDesc d = desc[s >> 1];
+        const int key = lpc_key(d, (int)(s & 1u));
+        if (key >= 0) perm[atomicAdd(&cursor[key + ((use_quads && lpc_quad(d, (int)(s & 1u), key)) ? 32 : 0)], 1u)] = s;
         lpc_flag[s] = key >= 0 ? 1 : 0;
     }
 }
@@ -241,16 +261,138 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
     return stalled;
 }
 
-// One LPC warp: streams perm[warp * 32 + lane].  hist: this warp's [32][32] int32 ring.
-template <bool kPoll, bool kPublish>
-__device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp, int32_t *hist_warp)
+// ---- four lanes per stream ---------------------------------------------------------------------
+// Lane r (0..3) of a quad owns taps j = r*T + t, t < T (T*4 >= order); eight streams per warp.  The
+// reference's early-exit loop over the taps (AlacFile.cs:322-331: newest coefficient index first, stop
+// when the running error changes sign) becomes a prefix problem: every tap's step
+// ((|d| + r) >> q) * (order - p) is computed unconditionally, the quad scans the steps in loop order
+// (lane 3's taps first), and tap p updates iff the error minus the steps BEFORE it is still positive.
+// Steps are clamped to 2^25 > max |error| (|e| <= 2^24 for rss <= 25), so the sums cannot wrap and a
+// clamped step still ends the loop.  Surplus taps (j >= order) carry weight 0, coefficient 0 and an
+// unreachable threshold, so they contribute nothing and never update.
+template <int T, bool kPoll, bool kPublish>
+__device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax, const int rss, const int ord,
+                                       const int q, const int16_t *__restrict__ coef16, const bool active,
+                                       int32_t *ring /* this quad's column of a [32][8] shared ring */,
+                                       const uint32_t *prog, uint32_t *done)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t n_active = a.perm_count[0];
+    const int r4 = lane & 3;
+    constexpr int32_t kClamp = 1 << 25;
+    int32_t c[T], H[T], wgt[T], thr[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+        const int j = r4 * T + t;
+        const bool valid = active && j < ord;
+        c[t] = valid ? (int32_t)coef16[j] : 0;
+        wgt[t] = valid ? ord - j : 0;                   // (order - p), AlacFile.cs:329
+        thr[t] = valid ? 0 : 0x7fffffff;
+        H[t] = 0;
+        asm volatile("" : "+r"(wgt[t]), "+r"(thr[t]));  // keep as register operands
+    }
+    const int32_t rnd = (int32_t)(1u << ((q - 1) & 31));            // :306 (quant 0 -> 1 << 31)
+    const uint32_t rneg = (1u << q) - 1u;                           // see lpc_warp
+    const int sh = (32 - rss) & 31;
+    int4 *row4 = reinterpret_cast<int4 *>(row);
+    const int nblk = (n + 3) >> 2, nblk_max = (nmax + 3) >> 2;
+
+    uint32_t avail = kPoll ? 0u : 0xFFFFFFFFu;
+    bool stalled = false;
+    if (kPoll) wait_avail(prog, (uint32_t)min(nblk, 10) * 4u, avail, active, stalled);
+    int4 cur = active ? __ldcg(row4) : make_int4(0, 0, 0, 0);
+    int4 nx1 = (active && nblk > 1) ? __ldcg(row4 + 1) : make_int4(0, 0, 0, 0);
+    int32_t prev = cur.x;                                           // o[i-1]; first sample always copies (:259-260)
+    if (r4 == 0) { H[0] = prev; ring[0] = prev; }
+    __syncwarp();
+    for (int b = 0; b < nblk_max; b++) {
+        if (kPoll && (b & 7) == 7) wait_avail(prog, (uint32_t)min(nblk, b + 11) * 4u, avail, active, stalled);
+        const int4 nx2 = (active && b + 2 < nblk) ? __ldcg(row4 + b + 2) : make_int4(0, 0, 0, 0);
+        int32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+#pragma unroll 1
+        for (int u = 0; u < 4; u++) {
+            const int i = b * 4 + u;
+            const int32_t e = u == 0 ? cur.x : (u == 1 ? cur.y : (u == 2 ? cur.z : cur.w));
+            int32_t o = prev;
+            if (i != 0) {
+                const int32_t base = ring[((uint32_t)(i - 1 - ord) & 31u) * 8];      // o[i-1-ord]
+                const bool main = i > ord;                                  // warm-up covers i = 1..ord (:284-293)
+                const int32_t nsg = e < 0 ? 1 : -1;                         // -sign(err)
+                const int32_t sgbase = e < 0 ? (int32_t)(0u - (uint32_t)base) : base;
+                const int32_t E0 = main ? (e < 0 ? (int32_t)(0u - (uint32_t)e) : e) : 0;   // sign(err) * err
+                const uint32_t rr = e < 0 ? rneg : 0u;
+                // pass 1: dot product and the unconditional steps of this lane's taps
+                uint32_t acc = 0;
+                int32_t dp[T], st[T];
+                int32_t mine = 0;
+#pragma unroll
+                for (int t = T - 1; t >= 0; --t) {
+                    dp[t] = (int32_t)((uint32_t)H[t] * (uint32_t)nsg + (uint32_t)sgbase);
+                    acc += (uint32_t)c[t] * (uint32_t)dp[t];
+                    const uint32_t mag = (uint32_t)abs(dp[t]) + rr;
+                    st[t] = (int32_t)min((mag >> q) * (uint32_t)wgt[t], (uint32_t)kClamp);
+                    mine += st[t];
+                }
+                // steps taken before this lane's first tap: the totals of the quad's HIGHER lanes
+                const int32_t t1 = __shfl_down_sync(0xffffffffu, mine, 1, 4);
+                const int32_t a1 = mine + (r4 < 3 ? t1 : 0);
+                const int32_t t2 = __shfl_down_sync(0xffffffffu, a1, 2, 4);
+                // (warm-up samples read a base that is not there yet: their steps are garbage, never used)
+                int32_t rem = main ? E0 - (a1 + (r4 < 2 ? t2 : 0) - mine) : -1;
+                // pass 2: sign-LMS update of the taps the reference's loop would have reached
+#pragma unroll
+                for (int t = T - 1; t >= 0; --t) {
+                    const int32_t sg = max(min(dp[t], 1), -1);
+                    c[t] -= rem > thr[t] ? sg : 0;
+                    rem -= st[t];
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2, 4);
+                const int32_t sum = (int32_t)(acc * (uint32_t)nsg);         // sum of (buf[b+order-j]-buf[b])*coef[j]
+                int32_t v = (int32_t)((uint32_t)rnd + (uint32_t)sum) >> q;  // :306-307
+                v = (int32_t)((uint32_t)v + (uint32_t)base + (uint32_t)e);  // :308
+                const int32_t w = (int32_t)((uint32_t)prev + (uint32_t)e);  // warm-up (:288)
+                const int32_t x = main ? v : w;
+                o = (int32_t)((uint32_t)x << sh) >> sh;                     // :309-310
+                // history: every lane shifts by one tap; lane r takes lane r-1's oldest value
+                const int32_t from_below = __shfl_up_sync(0xffffffffu, H[T - 1], 1, 4);
+#pragma unroll
+                for (int t = T - 1; t > 0; --t) H[t] = H[t - 1];
+                H[0] = r4 == 0 ? o : from_below;
+                if (r4 == 0) ring[((uint32_t)i & 31u) * 8] = o;
+                __syncwarp();
+                prev = o;
+            }
+            o0 = u == 0 ? o : o0; o1 = u == 1 ? o : o1; o2 = u == 2 ? o : o2; o3 = u == 3 ? o : o3;
+        }
+        if (active && r4 == 0 && b < nblk) row4[b] = make_int4(o0, o1, o2, o3);
+        if (kPublish && (b & 7) == 7) {              // hand-off to the pack warps, every 32 samples
+            __threadfence();
+            if (active && r4 == 0 && b < nblk) st_relaxed(done, (uint32_t)(b + 1) * 4u);
+        }
+        cur = nx1;
+        nx1 = nx2;
+    }
+    if (kPublish) {
+        __threadfence();
+        if (active && r4 == 0) st_relaxed(done, 0xFFFFFFFFu);
+    }
+    return stalled;
+}
+
+// One LPC warp.  The first ceil(n_quad / 8) warps take the four-lane streams (eight per warp), the
+// others 32 one-lane streams each.  hist_warp: this warp's 4 KB of shared memory.
+template <bool kPoll, bool kPublish>
+__device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int32_t *hist_warp)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_active = a.perm_count[0], n_quad = a.perm_count[1];
+    const uint32_t quad_warps = (n_quad + 7u) / 8u;
+    const bool quad = warp < quad_warps;
+    if (!quad) warp -= quad_warps;
     constexpr uint32_t SPW = ALACGPU_LPC_STREAMS_PER_WARP;
-    const uint32_t idx = warp * SPW + (uint32_t)lane;
-    if (warp * SPW >= n_active) return;
-    const bool active = idx < n_active && (uint32_t)lane < SPW;
+    const uint32_t idx = quad ? warp * 8u + (uint32_t)(lane >> 2) : warp * SPW + (uint32_t)lane;
+    if (!quad && warp * SPW >= n_active) return;
+    const bool active = quad ? idx < n_quad : (idx < n_active && (uint32_t)lane < SPW);
     int n = 0, rss = 32, ord = 31, q = 0;
     const int16_t *coef16 = nullptr;
     int32_t *row = nullptr;
@@ -258,7 +400,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
     uint32_t *done = nullptr;
     uint64_t f = 0;
     if (active) {
-        const uint32_t sid = a.perm[idx];
+        const uint32_t sid = quad ? a.perm[2u * a.n + idx] : a.perm[idx];
         f = a.f0 + (sid >> 1);
         const int ch = (int)(sid & 1u);
         const FrameDesc d = a.desc[f];
@@ -272,8 +414,20 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, const uint32_t warp
     const int need = active ? (ord == 31 ? 1 : ord) : 0;
     const int maxo = __reduce_max_sync(0xffffffffu, need);
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    int32_t *hist = hist_warp + lane;
     bool stalled;
+    if (quad) {
+        int32_t *ring = hist_warp + (lane >> 2);
+        if (!active) ord = 1;
+#define ALACGPU_LPC4(TT) stalled = lpc_warp4<TT, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, ring, prog, done)
+        if (maxo <= 20) ALACGPU_LPC4(5);
+        else if (maxo <= 24) ALACGPU_LPC4(6);
+        else if (maxo <= 28) ALACGPU_LPC4(7);
+        else ALACGPU_LPC4(8);
+#undef ALACGPU_LPC4
+        if (kPoll && active && stalled && (lane & 3) == 0) a.desc[f].status = FS_INTERNAL;
+        return;
+    }
+    int32_t *hist = hist_warp + lane;
 #define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, hist, prog, done)
     if (maxo <= 2) ALACGPU_LPC(2);
     else if (maxo <= 4) ALACGPU_LPC(4);

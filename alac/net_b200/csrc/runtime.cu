@@ -398,7 +398,8 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
     ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
-    ca.perm = s.perm.p; ca.perm_count = s.perm.p + 2u * (size_t)d.chunk_frames;
+    ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames;
+    ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC)) ? 1 : 0;
     const size_t cf2 = 2u * (size_t)d.chunk_frames;
     ca.progress = s.progress.p;
     ca.lpc_done = s.progress.p + cf2;
@@ -414,14 +415,14 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     }
     CU(cudaEventRecord(get_event(d, ev + 1), s.st));
     // fusion level: 2 = entropy + LPC + pack in one launch, 1 = entropy + LPC with K3 apart, 0 = three
-    // kernels.  Default: 2 when the inputs are resident (one launch does everything, and PCM can
-    // stream straight into a page-locked destination while the batch decodes: 8.4 vs 10.5 ms for
-    // configs[1]); 1 when chunks are being streamed in from the host (measured: the pack blocks'
-    // SM slots are better spent on the next chunks' producers, 11.7 vs 12.1 ms end to end).
+    // kernels.  Measured on configs[1] (one B200): level 1 is the fastest way to PCM in HBM (3.54 ms;
+    // the pack blocks of level 2 only get SM slots once producers retire: 4.23 ms) and while chunks are
+    // still being streamed in from the host (11.7 vs 12.1 ms end to end).  Level 2 pays when the PCM
+    // can stream straight into a page-locked destination while the batch is still decoding (resident
+    // inputs -> host PCM in 8.4 ms instead of kernels + 6.3 ms of D2H), so it is used exactly then.
     int fused = (ctx->opts.flags & ALACGPU_FLAG_NO_FUSION) ? 0 : (ctx->opts.flags & ALACGPU_FLAG_NO_PACK_FUSION) ? 1 : 2;
-    // ... and 1 again for chunks that fill the machine (> ~20k frames: issue-bound, no idle SMs for
-    // pack blocks to use; measured 59 vs 72 Gsamples/s on a 174k-frame batch).
-    if (fused == 2 && (streaming || c.n > kFullFusionMaxFrames)) fused = 1;
+    if (fused == 2 && !pcm_override && !(ctx->opts.flags & ALACGPU_FLAG_FORCE_PACK_FUSION)) fused = 1;
+    (void)streaming;
     if (pcm_override) { ca.pcm = pcm_override; ca.pcm_base = 0; }      // PCM straight into host-mapped memory
     if (with_decode) {
         CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
@@ -492,7 +493,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (decode)
             for (int s = 0; s < slots_used; s++) {
                 CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
-                CU(d.slots[s].perm.reserve((size_t)cf * 2u + 4u));
+                CU(d.slots[s].perm.reserve((size_t)cf * 4u + 4u));
                 CU(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
             }
         get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front

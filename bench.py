@@ -346,7 +346,7 @@ def run_ours(args):
         stage = {k: acc[k] / args.steps for k in acc}
         b_alg = comp_bytes + pcm_bytes
         fused = not (args.no_fusion or (args.flags & 2))
-        pack_fused = fused and not (args.flags & 4)
+        pack_fused = fused and bool(args.flags & 0x20) and not (args.flags & 4)
         names = {"entropy_ms": ("k123_decode (fused entropy + LPC + pack)" if pack_fused else
                                 "k12_entropy_lpc (fused entropy + LPC)") if fused else "k1_entropy",
                  "lpc_ms": "k2_lpc", "stereo_ms": "k3_stereo_pack"}

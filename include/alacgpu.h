@@ -97,6 +97,8 @@ typedef struct alacgpu_ctx alacgpu_ctx;
 #define ALACGPU_FLAG_KEEP_DEVICE_PCM 0x1u  /* keep decoded PCM resident in HBM after decode_all */
 #define ALACGPU_FLAG_NO_FUSION 0x2u        /* entropy, LPC and pack as three kernels instead of the fused, overlapped launch */
 #define ALACGPU_FLAG_NO_PACK_FUSION 0x4u   /* fuse entropy + LPC only; un-mix / pack stays a separate kernel */
+#define ALACGPU_FLAG_NO_QUAD_LPC 0x10u     /* one lane per stream for every LPC stream (no four-lane path for the tail-critical ones) */
+#define ALACGPU_FLAG_FORCE_PACK_FUSION 0x20u /* fully fused launch even when the PCM stays in HBM (tests / A-B runs) */
 #define ALACGPU_FLAG_NO_ZERO_COPY 0x8u     /* never write PCM straight into a page-locked destination; always device PCM + D2H copies */
 
 typedef struct alacgpu_opts {

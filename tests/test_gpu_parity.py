@@ -7,8 +7,11 @@ pytestmark = pytest.mark.gpu
 
 def _decode(tracks, dst=None, resident=False, **kw):
     """resident=False: decode_all streams the mdat in chunk by chunk (entropy + LPC fused, K3 apart);
-    resident=True: prepare() first, then ONE fully fused launch per chunk (entropy + LPC + pack)."""
+    resident=True: prepare() first, and (unless the test chose its own flags) force the fully fused
+    launch -- entropy + LPC + pack roles -- which the library otherwise keeps for zero-copy output."""
     from alac.net_b200 import BatchDecoder
+    if resident and "flags" not in kw:
+        kw["flags"] = 0x20
     with BatchDecoder(**kw) as dec:
         for t in tracks:
             dec.add_track(t.cfg, t.mdat, t.stsz)
@@ -82,7 +85,7 @@ def test_fused_and_two_kernel_paths_agree(flags, gen, oracle):
     """ALACGPU_FLAG_NO_FUSION (2): entropy and LPC as two launches; default: one fused launch in which
     the LPC warps consume residuals while the entropy lanes are still decoding"""
     tracks = gen.make_config(2, scale=0.02) + gen.make_config(1, scale=0.1) + gen.make_config(3, scale=0.1)
-    got, status, tm = _decode(tracks, flags=flags, resident=True)
+    got, status, tm = _decode(tracks, flags=flags | 0x20, resident=True)
     _assert_tracks_equal(tracks, got, status, oracle)
     # inputs resident: K123 + fix (default) / K12 + K3 (4) / K1 + K2 + K3 (2); K0 + sort ran in prepare / per chunk
     got, status, tm = _decode(tracks, flags=flags)
@@ -317,7 +320,7 @@ def test_random_payload_fuzz_matches_oracle(seed, gen, oracle):
         cfg = gen.TrackCfg(ss, cch, max_n, hm, ih, kmod, 44100)
         stsz = np.array([len(f) for f in frames], dtype=np.uint32)
         tracks.append(gen.Track(cfg, b"".join(frames), stsz, np.zeros(len(frames), np.int32), b""))
-    for flags, resident in ((0, True), (0, False), (2, False), (4, True)):
+    for flags, resident in ((0x20, True), (0, False), (2, False), (4, True), (0x10, False)):
         got, status, _ = _decode(tracks, flags=flags, resident=resident)
         _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
         assert (status == 0).any() and (status != 0).any()
