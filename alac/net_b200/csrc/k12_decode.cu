@@ -145,6 +145,13 @@ k3_fix_failed(const ChunkArgs a)
     for (uint32_t i = threadIdx.x; i < d.out_len; i += 128) dst[i] = 0;
 }
 
+// The entropy lanes skip over zero runs instead of writing them (k1_entropy.cuh): the chunk's rows
+// start out cleared, like the reference's output buffer (AlacFile.cs:238-245).
+static cudaError_t clear_planes(const ChunkArgs &a, cudaStream_t st)
+{
+    return cudaMemsetAsync(a.planes, 0, (size_t)a.n * 2u * a.ns * sizeof(int32_t), st);
+}
+
 static int lanes_log2_of(int lanes_per_warp)
 {
     if (lanes_per_warp == 16) return 4;
@@ -158,6 +165,7 @@ cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, u
     if (a.n == 0) return cudaSuccess;
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t warps = (a.n + (1u << lg) - 1) >> lg;
+    if (cudaError_t e = clear_planes(a, st)) return e;
     k1_entropy<<<(warps + 3) / 4, kK1Threads, 0, st>>>(a, lg);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -188,6 +196,7 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
     const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
+    if (cudaError_t e = clear_planes(a, st)) return e;
     k12_entropy_lpc<<<eblocks + (lwarps + 3) / 4, kK1Threads, 0, st>>>(a, lg, eblocks);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -205,6 +214,7 @@ cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st,
     const uint32_t tasks = ((a.max_sf + kPackGroup - 1) / kPackGroup) * a.n;
     static const uint32_t div = getenv("ALACGPU_PACK_DIV") ? (uint32_t)atoi(getenv("ALACGPU_PACK_DIV")) : 2400u;
     const uint32_t pblocks = tasks / div + 2u < 148u ? tasks / div + 2u : 148u;
+    if (cudaError_t e = clear_planes(a, st)) return e;
     k123_decode<<<eblocks + lblocks + pblocks, kK1Threads, 0, st>>>(a, lg, eblocks, lblocks);
     if (launches) *launches += 1;
     return cudaGetLastError();
