@@ -166,6 +166,122 @@ __device__ __forceinline__ void publish(uint32_t *p, uint32_t v)
 }
 constexpr uint32_t kStreamDone = 0xFFFFFFFFu;
 
+// ---- one decode step, in PTX ------------------------------------------------------------------------
+// The step is written in PTX so that it stays ~85 straight-line instructions (nvcc's version of the
+// same C juggled ten live booleans through P2R/R2P and came out at 150).  Operands:
+//   %0 cur  %1 nxt  %2 nn  %3 off  %4 wpos           bit cursor (BitCursor)
+//   %5 i    %6 nc   %7 h   %8 smm1 (signModifier-1)  output index, samples per channel, history
+//   %9 kk (k + 127)  %10 mk ((1<<k)-1)  %11 mm       parameters of the symbol at the cursor
+//   %12 R  %13 W                                      kind of that symbol: run length / raw field (0|1)
+//   %14 ring  %15 mult  %16 rssh (32-rss)  %17 kcap (kmod+127)  %18 kmask  %19 kk after a run  %20 row
+// Predicates inside: pA lane active, pesc nine 1 bits, pP raw field pending, pV a value completed,
+// pU a run length completed, pT a run-length symbol is next.
+#define ALACGPU_ENTROPY_STEP                                                                              \
+    /* the field at the cursor */                                                                        \
+    "shf.l.wrap.b32 w, %1, %0, %3;\n\t"                                                                   \
+    "shr.u32 t0, w, 23;\n\t"                                                                              \
+    "lop3.b32 fx, t0, 0x1FF, 0x4B000000, 0xBE;\n\t"   /* (~w >> 23) | 2^23-as-float */                   \
+    "add.rn.f32 fx, fx, 0fCB000000;\n\t"                                                                  \
+    "shr.b32 ex, fx, 23;\n\t"                          /* 127 + flo(~w >> 23); 0: nine 1 bits (:198) */   \
+    "setp.eq.u32 pesc, ex, 0;\n\t"                                                                        \
+    "sub.u32 x, 135, ex;\n\t"                          /* leading 1 bits */                               \
+    "sub.u32 s0, %9, ex;\n\t"                                                                             \
+    "add.u32 s0, s0, 8;\n\t"                           /* x + k */                                        \
+    "add.u32 s1, s0, 1;\n\t"                                                                              \
+    "shf.l.wrap.b32 e, w, 0, s1;\n\t"                                                                     \
+    "and.b32 e, e, %10;\n\t"                           /* the k bits after the terminator (:205) */       \
+    "max.u32 em, e, 1;\n\t"                                                                               \
+    "setp.ge.u32 pbig, e, 2;\n\t"                                                                         \
+    "mad.lo.u32 rice, x, %11, %8;\n\t"                                                                    \
+    "add.u32 rice, rice, em;\n\t"                      /* :206-210 (+ signModifier, :224) */              \
+    "selp.u32 rsh, 16, %16, pR;\n\t"                   /* raw field: 16 bits (:236) or rss (:224) */      \
+    "shr.u32 rawv, w, rsh;\n\t"                                                                           \
+    "add.u32 rawv, rawv, %8;\n\t"                                                                         \
+    "add.u32 rawv, rawv, 1;\n\t"                                                                          \
+    "selp.u32 dv, rawv, rice, pW;\n\t"                                                                    \
+    /* bits consumed: x + k (+1 if e >= 2, :210) | 9 | the raw field | 0 for an idle lane */             \
+    "setp.lt.u32 pA, %5, %6;\n\t"                                                                         \
+    "not.pred nA, pA;\n\t"                                                                                \
+    "sub.u32 alt, 32, rsh;\n\t"                                                                           \
+    "selp.u32 alt, alt, 9, pW;\n\t"                                                                       \
+    "selp.u32 alt, alt, 0, pA;\n\t"                                                                       \
+    "or.pred palt, pesc, pW;\n\t"                                                                         \
+    "or.pred palt, palt, nA;\n\t"                                                                         \
+    "add.u32 tb, %3, alt;\n\t"                                                                            \
+    "add.u32 ta, %3, s0;\n\t"                                                                             \
+    "@pbig add.u32 ta, ta, 1;\n\t"                                                                        \
+    "selp.u32 t, tb, ta, palt;\n\t"                                                                       \
+    /* move the cursor (BitCursor::seek) */                                                              \
+    "setp.ge.u32 prf, t, 32;\n\t"                                                                         \
+    "and.b32 %3, t, 31;\n\t"                                                                              \
+    "selp.u32 sel, 0x0123, 0x7654, prf;\n\t"                                                              \
+    "selp.u32 %0, %1, %0, prf;\n\t"                                                                       \
+    "prmt.b32 %1, %2, %1, sel;\n\t"                                                                       \
+    "and.b32 wa, %4, 63;\n\t"                                                                             \
+    "shl.b32 wa, wa, 2;\n\t"                                                                              \
+    "add.u32 wa, wa, %14;\n\t"                                                                            \
+    "@prf ld.shared.u32 %2, [wa];\n\t"                                                                    \
+    "@prf add.u32 %4, %4, 1;\n\t"                                                                         \
+    /* what was completed */                                                                             \
+    "not.pred nW, pW;\n\t"                                                                                \
+    "and.pred pP, pA, pesc;\n\t"                                                                          \
+    "and.pred pP, pP, nW;\n\t"                                                                            \
+    "not.pred nP, pP;\n\t"                                                                                \
+    "and.pred q0, pA, nP;\n\t"                                                                            \
+    "and.pred pU, q0, pR;\n\t"                                                                            \
+    "not.pred nR, pR;\n\t"                                                                                \
+    "and.pred pV, q0, nR;\n\t"                                                                            \
+    /* a value: output (:225-226) and history (:229) */                                                  \
+    "and.b32 t1, dv, 1;\n\t"                                                                              \
+    "neg.s32 t1, t1;\n\t"                                                                                 \
+    "shr.u32 t2, dv, 1;\n\t"                                                                              \
+    "xor.b32 t2, t2, t1;\n\t"                                                                             \
+    "mad.wide.u32 ad, %5, 4, %20;\n\t"                                                                    \
+    "@pV st.global.u32 [ad], t2;\n\t"                                                                     \
+    "mul.lo.u32 t3, %7, %15;\n\t"                                                                         \
+    "shr.s32 t3, t3, 9;\n\t"                                                                              \
+    "sub.s32 t3, %7, t3;\n\t"                                                                             \
+    "mad.lo.u32 hn, dv, %15, t3;\n\t"                                                                     \
+    "setp.gt.u32 pbv, dv, 0xFFFF;\n\t"                                                                    \
+    "selp.s32 hn, 0xFFFF, hn, pbv;\n\t"                                                                   \
+    /* output index: one value, or a run of dv zeros skipped (:240-245) */                               \
+    "add.u32 isum, %5, dv;\n\t"                                                                           \
+    "@pV add.u32 %5, %5, 1;\n\t"                                                                          \
+    "@pU mov.u32 %5, isum;\n\t"                                                                           \
+    "setp.lt.and.u32 pT, hn, 128, pV;\n\t"             /* :231 */                                         \
+    "setp.lt.and.u32 pT, %5, %6, pT;\n\t"                                                                 \
+    "setp.lt.and.s32 pF, hn, 0, pV;\n\t"               /* negative history: the lane stops here */        \
+    "@pF mov.u32 %6, 0;\n\t"                                                                              \
+    "@pV mov.s32 %7, hn;\n\t"                                                                             \
+    "@pT mov.s32 %7, 0;\n\t"                           /* :248 */                                         \
+    "@pV mov.u32 %8, 0xFFFFFFFF;\n\t"                                                                     \
+    "selp.u32 t4, 0xFFFFFFFF, 0, pbv;\n\t"                                                                \
+    "@pU mov.u32 %8, t4;\n\t"                          /* :233, :246 */                                   \
+    /* k of the next symbol: value (:221-222), run length (:234, clz(0) == 40), or after a run */        \
+    "shr.s32 t5, hn, 9;\n\t"                                                                              \
+    "add.s32 fk, t5, 0x4B000003;\n\t"                                                                     \
+    "add.rn.f32 fk, fk, 0fCB000000;\n\t"                                                                  \
+    "shr.b32 t5, fk, 23;\n\t"                                                                             \
+    "min.u32 kkv, t5, %17;\n\t"                                                                           \
+    "bfind.u32 t6, hn;\n\t"                                                                               \
+    "add.u32 t7, hn, 16;\n\t"                                                                             \
+    "shr.u32 t7, t7, 6;\n\t"                                                                              \
+    "sub.u32 t7, t7, t6;\n\t"                                                                             \
+    "add.u32 t7, t7, 134;\n\t"                                                                            \
+    "setp.eq.u32 pz, hn, 0;\n\t"                                                                          \
+    "selp.u32 t7, 143, t7, pz;\n\t"                                                                       \
+    "selp.u32 kn, %19, kkv, pU;\n\t"                                                                      \
+    "selp.u32 %9, t7, kn, pT;\n\t"                                                                        \
+    "shf.l.wrap.b32 t8, 2, 2, %9;\n\t"                 /* 1 << (kk - 127) */                              \
+    "sub.u32 %10, t8, 1;\n\t"                                                                             \
+    "selp.u32 t9, %18, 0xFFFFFFFF, pT;\n\t"                                                               \
+    "and.b32 %11, %10, t9;\n\t"                        /* :236 masks the multiplier */                    \
+    /* kind of the next field */                                                                         \
+    "and.pred q0, pP, pR;\n\t"                                                                            \
+    "and.pred q1, nP, pT;\n\t"                                                                            \
+    "or.pred pR, q0, q1;\n\t"                                                                             \
+    "mov.pred pW, pP;\n\t"
+
 // One block of 128 threads = 4 entropy warps.  `block` is the index among the entropy blocks;
 // ring_smem: kRingBytes * kK1Threads bytes, 256-byte aligned.  The planes must be zero on entry.
 template <bool kPublish>
@@ -183,12 +299,14 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     work = work && d.status == FS_OK && !(d.flags & FF_ESCAPE) && d.n > 0;   // escape frames are read directly by K3
     const FrameRef ref = a.refs[f];
     const TrackCfg cfg = a.cfgs[ref.track];
-    const uint32_t nc = work ? (uint32_t)d.n : 0u;            // samples per channel
+    const uint32_t n = work ? (uint32_t)d.n : 0u;             // samples per channel
     const uint32_t rssh = 32u - (uint32_t)d.rss;              // the raw field after nine 1 bits is rss bits (:198-202)
     const uint32_t kmod = (uint32_t)cfg.rice_kmodifier;
     const uint32_t kmask = (1u << kmod) - 1u;                 // AlacFile.cs:483,:643
     const uint32_t kcap = kmod + 127u;
+    const uint32_t kk_after_run = min(128u, kcap);            // history 0: k = min(flo(3), kmod)
     const int32_t h0 = cfg.rice_initial_history;              // :216
+    const uint32_t kk0 = min(exp_of(0x4B000000u | (uint32_t)((h0 >> 9) + 3)), kcap);   // :221-222
 
     BitCursor br;
     br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull, ring_smem + threadIdx.x * (uint32_t)kRingBytes);
@@ -199,19 +317,19 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     uint32_t *prog = a.progress + (uint64_t)(work ? slot : 0u) * 2u;
     uint32_t mult = (uint32_t)((int32_t)d.rice_mod[0] * (cfg.rice_history_mult / 4));   // :483
     uint32_t i = 0;                          // output index of the next value
+    uint32_t nc = n;                         // 0 once the lane has stopped on a fault
     int32_t h = h0;
     uint32_t smm1 = 0xFFFFFFFFu;             // signModifier - 1
-    uint32_t k = min(exp_of(0x4B000000u | (uint32_t)((h0 >> 9) + 3)), kcap) - 127u;   // :221-222
-    uint32_t mk = (1u << k) - 1u;            // mask of the k-bit field
+    uint32_t kk = kk0;                       // k + 127
+    uint32_t mk = (1u << (kk - 127u)) - 1u;  // mask of the k-bit field
     uint32_t mm = mk;                        // multiplier of the unary part (:206; & kmask for a run length, :236)
-    bool runmode = false;                    // the symbol at the cursor is a zero-run length (:234-236)
-    bool israw = false;                      // the field at the cursor is the raw one after nine 1 bits
-    bool active = work;                      // the lane has a symbol to decode in its current channel
+    uint32_t R = 0, W = 0;                   // the field at the cursor is a zero-run length (:234-236) / a raw field
     uint8_t status = FS_OK;
 
     for (uint32_t period = 0;; ++period) {
         br.top_up();
         cp_async_wait<1>();                  // everything but the group just committed
+        const bool active = i < nc;
         if (kPublish && (period & 1u)) {     // every 32 steps
             __threadfence();
             if (active) publish(prog, i);
@@ -219,6 +337,8 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
         // channel hand-over: a lane that ended its channel (or faulted) during the last period
         if (__any_sync(0xffffffffu, chans != 0u && !active)) {
             if (chans != 0u && !active) {
+                if (h < 0) status = FS_HISTORY;                                   // reference: garbage k
+                else if (i > (uint32_t)kMaxFrameSamples) status = FS_RUN_OVERFLOW;   // reference: IndexOutOfRange
                 const bool dead = status != FS_OK;
                 if (kPublish) {              // a faulted lane releases the consumers of all its streams
                     __threadfence();
@@ -226,70 +346,42 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
                     if (dead && chans == 2u) publish(prog + 1, kStreamDone);
                 }
                 chans = dead ? 0u : chans - 1u;
+                nc = 0;
                 if (chans != 0u) {           // channel B starts where A ended (:653)
                     row += a.ns;
                     prog += 1;
                     mult = (uint32_t)((int32_t)d.rice_mod[1] * (cfg.rice_history_mult / 4));
                     i = 0;
+                    nc = n;
                     h = h0;
                     smm1 = 0xFFFFFFFFu;
-                    k = min(exp_of(0x4B000000u | (uint32_t)((h0 >> 9) + 3)), kcap) - 127u;
-                    mk = (1u << k) - 1u;
+                    kk = kk0;
+                    mk = (1u << (kk - 127u)) - 1u;
                     mm = mk;
-                    runmode = israw = false;
-                    active = true;
+                    R = W = 0;
                 }
             }
         }
         if (!__any_sync(0xffffffffu, chans != 0u)) break;
 
-#pragma unroll 4
-        for (int u = 0; u < kPeriod; u++) {
-            // ---- the field at the cursor -------------------------------------------------------
-            const uint32_t w = br.peek();
-            const uint32_t ex = exp_of(((w >> 23) ^ 0x1FFu) | 0x4B000000u);   // 127 + flo(~w >> 23); 0: nine 1 bits
-            const bool esc = ex == 0u;                                        // :198
-            const uint32_t x = 135u - ex;                                     // leading 1 bits (0..8)
-            const uint32_t s1 = x + k + 1u;                                   // unary part, terminator, k bits
-            const uint32_t e = __funnelshift_l(w, 0u, s1) & mk;               // the k bits (:205)
-            const uint32_t em = max(e, 1u);
-            const uint32_t rice = x * mm + smm1 + em;                         // :206-210 (+ signModifier, :224)
-            const uint32_t rawsh = runmode ? 16u : rssh;                      // :236 reads 16 raw bits, :224 rss
-            const uint32_t rawv = (w >> rawsh) + (smm1 + 1u);
-            const uint32_t dv = israw ? rawv : rice;
-            uint32_t cons = s1 - (e < 2u ? 1u : 0u);                          // x + k, one more if e >= 2 (:210)
-            cons = esc ? 9u : cons;
-            cons = israw ? 32u - rawsh : cons;
-            cons = active ? cons : 0u;
-            br.seek(br.off + cons);
-            const bool pend = active && esc && !israw;                        // raw field next step
-            const bool done = active && !pend;
-            const bool isval = done && !runmode;
-            const bool isrun = done && runmode;
-            // ---- a value: output, history (:225-229) -------------------------------------------
-            if (isval) row[i] = (int32_t)(dv >> 1) ^ -(int32_t)(dv & 1u);
-            const int32_t hb = h - ((int32_t)((uint32_t)h * mult) >> 9);
-            int32_t hn = (int32_t)(dv * mult + (uint32_t)hb);
-            hn = dv > 0xFFFFu ? 0xFFFF : hn;
-            const uint32_t i1 = i + (isval ? 1u : 0u) + (isrun ? dv : 0u);    // a run of dv zeros is skipped (:240-245)
-            const bool hfault = isval && hn < 0;                              // reference: garbage k
-            const bool rfault = isrun && dv != 0u && i + dv > (uint32_t)kMaxFrameSamples;   // reference: IndexOutOfRange
-            const bool torun = isval && (uint32_t)hn < 128u && i1 < nc;       // :231
-            // ---- parameters of the next symbol -------------------------------------------------
-            h = isval ? (torun ? 0 : hn) : h;                                 // :248 (h stays 0 through the run symbol)
-            smm1 = isval ? 0xFFFFFFFFu : isrun ? (dv > 0xFFFFu ? 0xFFFFFFFFu : 0u) : smm1;   // :233,:246
-            const uint32_t kv = min(exp_of((uint32_t)((h >> 9) + 0x4B000003)), kcap) - 127u;   // :221-222
-            const uint32_t hz = (uint32_t)hn & 127u;
-            const uint32_t kz = hz == 0u ? 16u : 134u - exp_of(hz | 0x4B000000u) + ((hz + 16u) >> 6);   // :234 (clz(0) == 40)
-            k = torun ? kz : kv;
-            mk = (1u << k) - 1u;
-            mm = torun ? (mk & kmask) : mk;
-            runmode = pend ? runmode : torun;
-            israw = pend;
-            if (hfault) status = FS_HISTORY;
-            if (rfault) status = FS_RUN_OVERFLOW;
-            i = i1;
-            active = active && !hfault && !rfault && i1 < nc;
+#pragma unroll 1
+        for (int u = 0; u < kPeriod; u += 4) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred pR, pW, pA, nA, pesc, pbig, palt, prf, pP, nP, nW, nR, pV, pU, pT, pF, pbv, pz, q0, q1;\n\t"
+                ".reg .b32 w, t0, fx, ex, x, s0, s1, e, em, rice, rsh, rawv, dv, alt, tb, ta, t, sel, wa;\n\t"
+                ".reg .b32 t1, t2, t3, hn, isum, t4, t5, fk, kkv, t6, t7, kn, t8, t9;\n\t"
+                ".reg .b64 ad;\n\t"
+                "setp.ne.u32 pR, %12, 0;\n\t"
+                "setp.ne.u32 pW, %13, 0;\n\t"
+                ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_STEP
+                "selp.u32 %12, 1, 0, pR;\n\t"
+                "selp.u32 %13, 1, 0, pW;\n\t"
+                "}"
+                : "+r"(br.cur), "+r"(br.nxt), "+r"(br.nn), "+r"(br.off), "+r"(br.wpos), "+r"(i), "+r"(nc), "+r"(h),
+                  "+r"(smm1), "+r"(kk), "+r"(mk), "+r"(mm), "+r"(R), "+r"(W)
+                : "r"(br.ring), "r"(mult), "r"(rssh), "r"(kcap), "r"(kmask), "r"(kk_after_run), "l"(row)
+                : "memory");
         }
     }
     cp_async_wait<0>();            // nothing may land in the ring after this block's shared memory is reused
