@@ -22,7 +22,9 @@
 // LOWER block indices and are therefore resident or finished by the time it
 // runs (the same assumption decoupled look-back scans rest on); the wait is
 // bounded anyway and flags ALACGPU_FRAME_INTERNAL instead of hanging.
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "k1_entropy.cuh"
 #include "k2_lpc.cuh"
@@ -47,16 +49,39 @@ k2_lpc(const ChunkArgs a)
 
 static_assert(kK1Threads == kK2Threads, "the fused kernel uses one block size for both roles");
 
+// Debug aid (ALACGPU_TRACE=<file>): per-warp [start, end] of the fused launch in globaltimer ns, and the SM.
+__device__ unsigned long long *g_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_warp(unsigned long long t0)
+{
+    unsigned long long *tr = g_trace;
+    if (tr && (threadIdx.x & 31) == 0) {
+        const uint32_t w = blockIdx.x * (kK1Threads / 32) + (threadIdx.x >> 5);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[3 * w] = t0;
+        tr[3 * w + 1] = gtime();
+        tr[3 * w + 2] = smid;
+    }
+}
+
 __global__ void __launch_bounds__(kK1Threads, 3)
 k12_entropy_lpc(const ChunkArgs a, const int lanes_log2, const uint32_t n_eblocks)
 {
     __shared__ __align__(256) uint8_t smem[kRingBytes * kK1Threads];      // 32 KB: bit rings, or 16 KB of LPC history
+    const unsigned long long t0 = gtime();
     if (blockIdx.x < n_eblocks) {
         entropy_block<true>(a, lanes_log2, blockIdx.x, smem);
     } else {
         const uint32_t warp = ((blockIdx.x - n_eblocks) * kK2Threads + threadIdx.x) >> 5;
         lpc_role<true, false>(a, warp, reinterpret_cast<int32_t *>(smem) + (threadIdx.x >> 5) * 1024);
     }
+    trace_warp(t0);
 }
 
 // ---- pack role of the fully fused launch ---------------------------------------------------------
@@ -152,6 +177,13 @@ static cudaError_t clear_planes(const ChunkArgs &a, cudaStream_t st)
     return cudaMemsetAsync(a.planes, 0, (size_t)a.n * 2u * a.ns * sizeof(int32_t), st);
 }
 
+// upper bound of the four-lane warps (eight streams each); warps past the work lists exit at once
+static uint32_t quad_warp_bound(const ChunkArgs &a)
+{
+    const uint32_t per_frame = ((a.use_quads & 255) ? 1u : 0u) + ((a.use_quads >> 8) & 255 ? 1u : 0u);
+    return (a.n * per_frame + 7u) / 8u;
+}
+
 static int lanes_log2_of(int lanes_per_warp)
 {
     if (lanes_per_warp == 16) return 4;
@@ -183,7 +215,7 @@ cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
     // upper bound; warps past the work lists exit at once
-    const uint32_t warps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
+    const uint32_t warps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + quad_warp_bound(a);
     k2_lpc<<<(warps + 3) / 4, kK2Threads, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -195,9 +227,32 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
+    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + quad_warp_bound(a);
     if (cudaError_t e = clear_planes(a, st)) return e;
-    k12_entropy_lpc<<<eblocks + (lwarps + 3) / 4, kK1Threads, 0, st>>>(a, lg, eblocks);
+    const uint32_t grid = eblocks + (lwarps + 3) / 4;
+    static const char *trace_path = getenv("ALACGPU_TRACE");
+    unsigned long long *tr = nullptr;
+    if (trace_path && a.n >= 4096) {          // debug: one whole-batch launch, synchronous
+        cudaMalloc(&tr, (size_t)grid * 12 * sizeof(unsigned long long));
+        cudaMemset(tr, 0, (size_t)grid * 12 * sizeof(unsigned long long));
+        cudaMemcpyToSymbol(g_trace, &tr, sizeof(tr));
+    }
+    k12_entropy_lpc<<<grid, kK1Threads, 0, st>>>(a, lg, eblocks);
+    if (tr) {
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h((size_t)grid * 12);
+        cudaMemcpy(h.data(), tr, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> cnt(2);
+        cudaMemcpy(cnt.data(), a.perm_count, 8, cudaMemcpyDeviceToHost);
+        if (FILE *fp = fopen(trace_path, "w")) {
+            fprintf(fp, "# eblocks %u grid %u one_lane_streams %u quad_streams %u\n", eblocks, grid, cnt[0], cnt[1]);
+            for (size_t w = 0; w < (size_t)grid * 4; w++) fprintf(fp, "%zu %llu %llu %llu\n", w, h[3 * w], h[3 * w + 1], h[3 * w + 2]);
+            fclose(fp);
+        }
+        unsigned long long *none = nullptr;
+        cudaMemcpyToSymbol(g_trace, &none, sizeof(none));
+        cudaFree(tr);
+    }
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -208,7 +263,7 @@ cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st,
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + (a.use_quads ? (a.n + 7u) / 8u : 0u);
+    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + quad_warp_bound(a);
     const uint32_t lblocks = (lwarps + 3) / 4;
     // pack blocks: one per ~2400 tasks (a task is ~2.5 us of one warp, the decode stages leave ~2.5 ms)
     const uint32_t tasks = ((a.max_sf + kPackGroup - 1) / kPackGroup) * a.n;

@@ -52,12 +52,13 @@ __device__ __forceinline__ int lpc_key(const FrameDesc &d, int ch)
 // the entropy lane has finished the other channel, and its order-30 recurrence is the slowest thing
 // in the pipeline, so these streams get FOUR lanes each (lpc_warp4) instead of one.  The rest of the
 // streams have slack and stay one lane per stream.
-constexpr int kQuadMinOrder = 17;
-
-__device__ __forceinline__ bool lpc_quad(const FrameDesc &d, int ch, int key)
+// `use_quads` packs the two thresholds: bits 0..7 = smallest order that gets four lanes on the LAST
+// channel of a frame, bits 8..15 = the same for the other channel; 0 = never.
+__device__ __forceinline__ bool lpc_quad(const FrameDesc &d, int ch, int key, int use_quads)
 {
     const int last = (d.flags & FF_STEREO) ? 1 : 0;
-    return key >= kQuadMinOrder && ch == last;
+    const int thr = ch == last ? (use_quads & 255) : ((use_quads >> 8) & 255);
+    return thr != 0 && key >= thr;
 }
 
 // perm[0 .. n_rest): one-lane streams, heaviest first; perm[2n .. 2n + n_quad): four-lane streams,
@@ -73,7 +74,7 @@ k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *
     for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
         const FrameDesc d = desc[s >> 1];
         const int key = lpc_key(d, (int)(s & 1u));
-        if (key >= 0) atomicAdd(&hist[key + ((use_quads && lpc_quad(d, (int)(s & 1u), key)) ? 32 : 0)], 1u);
+        if (key >= 0) atomicAdd(&hist[key + (lpc_quad(d, (int)(s & 1u), key, use_quads) ? 32 : 0)], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -89,7 +90,7 @@ k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *
     for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
         const FrameDesc d = desc[s >> 1];
         const int key = lpc_key(d, (int)(s & 1u));
-        if (key >= 0) perm[atomicAdd(&cursor[key + ((use_quads && lpc_quad(d, (int)(s & 1u), key)) ? 32 : 0)], 1u)] = s;
+        if (key >= 0) perm[atomicAdd(&cursor[key + (lpc_quad(d, (int)(s & 1u), key, use_quads) ? 32 : 0)], 1u)] = s;
         lpc_flag[s] = key >= 0 ? 1 : 0;
     }
 }
@@ -419,7 +420,10 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
         int32_t *ring = hist_warp + (lane >> 2);
         if (!active) ord = 1;
 #define ALACGPU_LPC4(TT) stalled = lpc_warp4<TT, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, ring, prog, done)
-        if (maxo <= 20) ALACGPU_LPC4(5);
+        if (maxo <= 8) ALACGPU_LPC4(2);
+        else if (maxo <= 12) ALACGPU_LPC4(3);
+        else if (maxo <= 16) ALACGPU_LPC4(4);
+        else if (maxo <= 20) ALACGPU_LPC4(5);
         else if (maxo <= 24) ALACGPU_LPC4(6);
         else if (maxo <= 28) ALACGPU_LPC4(7);
         else ALACGPU_LPC4(8);

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -139,6 +140,10 @@ struct alacgpu_ctx {
     uint32_t max_sf = 0;                  // most sample-frames any frame emits
     uint32_t index_launches = 0;
     alacgpu_timing timing{};
+    // stage timings of the last pipeline are read back from its CUDA events on demand (alacgpu_get_timing):
+    // ~80 event queries are not on the caller's critical path
+    bool timing_pending = false;
+    bool tp_stage = false, tp_index = false, tp_decode = false, tp_d2h = false, tp_zc = false;
     std::string err;
     std::vector<int32_t> h_status;
     bool have_status = false;
@@ -399,7 +404,16 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
     ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
     ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames;
-    ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC)) ? 1 : 0;
+    {
+        // four-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
+        // streams from order 17 up (measured best on configs[1]: 2.72 ms; both channels 3.1 ms -- the extra
+        // warps slow the entropy lanes down).  While chunks stream in from the host the GPU has slack and
+        // the first PCM should leave as early as possible: both channels (end to end 9.9 -> 9.65 ms).
+        static const int q_last = getenv("ALACGPU_QUAD_MIN_LAST") ? atoi(getenv("ALACGPU_QUAD_MIN_LAST")) : 17;
+        static const int q_first = getenv("ALACGPU_QUAD_MIN_FIRST") ? atoi(getenv("ALACGPU_QUAD_MIN_FIRST")) : -1;
+        const int qf = q_first >= 0 ? q_first : (streaming ? 17 : 0);
+        ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC)) ? ((q_last & 255) | ((qf & 255) << 8)) : 0;
+    }
     const size_t cf2 = 2u * (size_t)d.chunk_frames;
     ca.progress = s.progress.p;
     ca.lpc_done = s.progress.p + cf2;
@@ -422,7 +436,6 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     // inputs -> host PCM in 8.4 ms instead of kernels + 6.3 ms of D2H), so it is used exactly then.
     int fused = (ctx->opts.flags & ALACGPU_FLAG_NO_FUSION) ? 0 : (ctx->opts.flags & ALACGPU_FLAG_NO_PACK_FUSION) ? 1 : 2;
     if (fused == 2 && !pcm_override && !(ctx->opts.flags & ALACGPU_FLAG_FORCE_PACK_FUSION)) fused = 1;
-    (void)streaming;
     if (pcm_override) { ca.pcm = pcm_override; ca.pcm_base = 0; }      // PCM straight into host-mapped memory
     if (with_decode) {
         CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
@@ -444,8 +457,61 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
 
 // The whole pipeline on every device.  stage: copy mdat to the arena (chunk by chunk);
 // index: run K0; decode: run K1-K3; pcm_dst: copy PCM back chunk by chunk.
+// Stage timings of the last pipeline, from the CUDA events its streams recorded (max over devices).
+void finish_timing(alacgpu_ctx *ctx)
+{
+    if (!ctx->timing_pending) return;
+    ctx->timing_pending = false;
+    const bool stage = ctx->tp_stage, index = ctx->tp_index, decode = ctx->tp_decode, to_host = ctx->tp_d2h && !ctx->tp_zc;
+    float k0 = 0, k1 = 0, k2 = 0, k3 = 0, kall = 0, d2h = 0, h2d = 0;
+    for (Device &d : ctx->devs) {
+        if (d.f_hi == d.f_lo || d.chunks.empty()) continue;
+        cudaSetDevice(d.id);
+        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, ms = 0;
+        for (size_t ci = 0; ci < d.chunks.size(); ci++) {
+            const size_t ev = kEvBase + ci * kEvPerChunk;
+            cudaEventElapsedTime(&ms, d.events[ev], d.events[ev + 1]); s0 += ms;
+            cudaEventElapsedTime(&ms, d.events[ev + 1], d.events[ev + 2]); s1 += ms;
+            cudaEventElapsedTime(&ms, d.events[ev + 2], d.events[ev + 3]); s2 += ms;
+            cudaEventElapsedTime(&ms, d.events[ev + 3], d.events[ev + 4]); s3 += ms;
+        }
+        static const bool dump = getenv("ALACGPU_HOST_TIMING") != nullptr;
+        if (dump) {            // debug: the pipeline's schedule, ms from its start
+            for (size_t ci = 0; ci < d.chunks.size(); ci++) {
+                const size_t ev = kEvBase + ci * kEvPerChunk;
+                float a = 0, b = 0, c2 = 0, e2 = 0, h = 0;
+                if (stage) cudaEventElapsedTime(&h, d.events[0], d.events[ev + 5]);
+                cudaEventElapsedTime(&a, d.events[0], d.events[ev]);
+                cudaEventElapsedTime(&b, d.events[0], d.events[ev + 1]);
+                cudaEventElapsedTime(&c2, d.events[0], d.events[ev + 2]);
+                cudaEventElapsedTime(&e2, d.events[0], d.events[ev + 4]);
+                fprintf(stderr, "[alacgpu] chunk %2zu n %5u h2d-done %6.2f start %6.2f k0-done %6.2f k12-done %6.2f k3-done %6.2f\n",
+                        ci, d.chunks[ci].n, h, a, b, c2, e2);
+            }
+            if (to_host) { float x = 0; cudaEventElapsedTime(&x, d.events[0], d.events[3]); fprintf(stderr, "[alacgpu] d2h-done %6.2f\n", x); }
+        }
+        cudaEventElapsedTime(&ms, d.events[0], d.events[1]);
+        k0 = std::max(k0, s0); k1 = std::max(k1, s1); k2 = std::max(k2, s2); k3 = std::max(k3, s3);
+        kall = std::max(kall, ms);
+        if (to_host) { cudaEventElapsedTime(&ms, d.events[2], d.events[3]); d2h = std::max(d2h, ms); }
+        if (stage) {
+            cudaEventElapsedTime(&ms, d.events[0], d.events[kEvBase + (d.chunks.size() - 1) * kEvPerChunk + 5]);
+            h2d = std::max(h2d, ms);
+        }
+    }
+    cudaGetLastError();
+    alacgpu_timing &tm = ctx->timing;
+    if (index) tm.index_ms = k0;
+    if (decode) { tm.entropy_ms = k1; tm.lpc_ms = k2; tm.stereo_ms = k3; }
+    tm.kernels_ms = kall;
+    if (stage) tm.h2d_ms = h2d;
+    if (ctx->tp_d2h) tm.d2h_ms = to_host ? d2h : 0.f;
+}
+
 int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint8_t *pcm_dst, uint32_t *launches_out)
 {
+    finish_timing(ctx);          // the events are about to be re-recorded
+    const double t_enter = now_ms();
     const int n_dev = (int)ctx->devs.size();
     uint32_t launches = 0, chunks_total = 0;
     // Zero-copy output: when the caller's buffer is page-locked and mapped (alacgpu_host_alloc, or any
@@ -530,7 +596,8 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (pcm_dst && !zc) CU(cudaEventRecord(d.events[3], d.st_d2h));
     }
     // ---- wait + timings --------------------------------------------------------
-    float k0 = 0, k1 = 0, k2 = 0, k3 = 0, kall = 0, d2h = 0, h2d = 0;
+    const double t_issued = now_ms();
+    double t_synced = 0;
     for (int g = 0; g < n_dev; g++) {
         Device &d = ctx->devs[g];
         if (d.f_hi == d.f_lo) continue;
@@ -538,22 +605,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         CU(cudaStreamSynchronize(d.slots[0].st));
         if (pcm_dst && !zc) CU(cudaStreamSynchronize(d.st_d2h));
         if (stage) CU(cudaStreamSynchronize(d.st_h2d));
-        float s0 = 0, s1 = 0, s2 = 0, s3 = 0, ms = 0;
-        for (size_t ci = 0; ci < d.chunks.size(); ci++) {
-            const size_t ev = kEvBase + ci * kEvPerChunk;
-            cudaEventElapsedTime(&ms, d.events[ev], d.events[ev + 1]); s0 += ms;
-            cudaEventElapsedTime(&ms, d.events[ev + 1], d.events[ev + 2]); s1 += ms;
-            cudaEventElapsedTime(&ms, d.events[ev + 2], d.events[ev + 3]); s2 += ms;
-            cudaEventElapsedTime(&ms, d.events[ev + 3], d.events[ev + 4]); s3 += ms;
-        }
-        cudaEventElapsedTime(&ms, d.events[0], d.events[1]);
-        k0 = std::max(k0, s0); k1 = std::max(k1, s1); k2 = std::max(k2, s2); k3 = std::max(k3, s3);
-        kall = std::max(kall, ms);
-        if (pcm_dst && !zc) { cudaEventElapsedTime(&ms, d.events[2], d.events[3]); d2h = std::max(d2h, ms); }
-        if (stage) {
-            cudaEventElapsedTime(&ms, d.events[0], d.events[kEvBase + (d.chunks.size() - 1) * kEvPerChunk + 5]);
-            h2d = std::max(h2d, ms);
-        }
+        t_synced = now_ms();
         if (stage || index) d.resident = true;
         if (decode) { d.decoded = true; d.pcm_resident = !zc; }     // zero-copy output leaves no PCM in HBM
         if (index) {
@@ -562,13 +614,11 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
             if (mism) return fail(ctx, ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size");
         }
     }
-    alacgpu_timing &tm = ctx->timing;
-    if (index) tm.index_ms = k0;
-    if (decode) { tm.entropy_ms = k1; tm.lpc_ms = k2; tm.stereo_ms = k3; }
-    tm.kernels_ms = kall;
-    if (stage) tm.h2d_ms = h2d;
-    if (pcm_dst) tm.d2h_ms = zc ? 0.f : d2h;
-    tm.chunks = chunks_total;
+    if (getenv("ALACGPU_HOST_TIMING"))
+        fprintf(stderr, "[alacgpu] run_pipeline: issue %.3f ms, wait %.3f ms, after %.3f ms\n", t_issued - t_enter, t_synced - t_issued, now_ms() - t_synced);
+    ctx->timing_pending = true;
+    ctx->tp_stage = stage; ctx->tp_index = index; ctx->tp_decode = decode; ctx->tp_d2h = pcm_dst != nullptr; ctx->tp_zc = zc != nullptr;
+    ctx->timing.chunks = chunks_total;
     if (launches_out) *launches_out = launches;
     ctx->have_status = false;
     return ALACGPU_OK;
@@ -834,6 +884,7 @@ int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uin
     const double t0 = now_ms();
     int32_t r = build_plan(ctx);
     if (r) return r;
+    if (getenv("ALACGPU_HOST_TIMING")) fprintf(stderr, "[alacgpu] build_plan %.3f ms\n", now_ms() - t0);
     const bool resident = all_resident(ctx);
     if (!resident) { ctx->timing = alacgpu_timing{}; ctx->index_launches = 0; }
     // not yet staged: stream mdat in, index and decode chunk by chunk; else decode only
@@ -843,6 +894,7 @@ int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uin
     fill_totals(ctx);
     ctx->timing.kernel_launches = ctx->index_launches + launches;
     ctx->timing.total_ms = (float)(now_ms() - t0);
+    if (getenv("ALACGPU_HOST_TIMING")) fprintf(stderr, "[alacgpu] decode_all %.3f ms\n", now_ms() - t0);
     for (size_t t = 0; t < ctx->tracks.size(); t++) {
         if (track_pcm_off) track_pcm_off[t] = ctx->tracks[t].pcm_off;
         if (track_pcm_len) track_pcm_len[t] = ctx->tracks[t].pcm_len;
@@ -971,6 +1023,7 @@ int32_t alacgpu_track_pcm_bytes(alacgpu_ctx *ctx, int32_t track, uint64_t *off, 
 int32_t alacgpu_get_timing(alacgpu_ctx *ctx, alacgpu_timing *out)
 {
     if (!ctx || !out) return ALACGPU_ERR_INVALID_ARG;
+    finish_timing(ctx);
     *out = ctx->timing;
     return ALACGPU_OK;
 }
