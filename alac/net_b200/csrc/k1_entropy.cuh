@@ -158,7 +158,7 @@ struct BitCursor {
 };
 
 // Progress hand-off to the LPC warps of the fused kernel (k12_decode.cu): a lane publishes how
-// many residuals of its stream are in the plane (every 32 steps: fence, then a relaxed store the
+// many residuals of its stream are in the plane (every 64 steps: fence, then a relaxed store the
 // consumer reads with ld.acquire) and 0xFFFFFFFF when the channel is complete.
 __device__ __forceinline__ void publish(uint32_t *p, uint32_t v)
 {
@@ -330,7 +330,8 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
         br.top_up();
         cp_async_wait<1>();                  // everything but the group just committed
         const bool active = i < nc;
-        if (kPublish && (period & 1u)) {     // every 32 steps
+        if (kPublish && (period & 3u) == 3u) {   // every 64 steps (the fence waits for the lane's stores: ~15 % of the
+                                                 // stage when done every 32)
             __threadfence();
             if (active) publish(prog, i);
         }

@@ -152,6 +152,9 @@ constexpr uint32_t kSpinLimit = 1u << 22;   // x (256 ns sleep + one L2 round tr
 __device__ __forceinline__ void wait_avail(const uint32_t *prog, const uint32_t need, uint32_t &avail,
                                            const bool active, bool &stalled)
 {
+    // Back-off: a consumer of channel B sits here for the whole of channel A's entropy decode, and every
+    // poll costs issue slots (and an L1 invalidation) that the entropy lanes of the same SM need.
+    uint32_t ns = 256;
     for (uint32_t spins = 0;; ++spins) {
         if (active && avail < need) avail = ld_acquire(prog);
         const bool ok = !active || avail >= need;
@@ -161,7 +164,8 @@ __device__ __forceinline__ void wait_avail(const uint32_t *prog, const uint32_t 
             avail = 0xFFFFFFFFu;
             break;
         }
-        __nanosleep(256);
+        __nanosleep(ns);
+        ns = min(ns * 2u, 4096u);
     }
 }
 

@@ -222,10 +222,11 @@ def batch_leg(args, local):
             tm = dec.timing()
             ms.append(tm["index_ms"] + tm["kernels_ms"])
         t_ms = float(np.median(ms))
+        stage = {k: tm[k] for k in ("index_ms", "entropy_ms", "lpc_ms", "stereo_ms", "kernels_ms", "chunks")}
     comp = sum(len(t.mdat) for t in tracks)
     pcm = sum(len(t.pcm) for t in tracks)
     return {"workload": desc, "frames": sum(t.n_frames for t in tracks), "samples": samples,
-            "device_ms": t_ms, "value": samples / (t_ms * 1e-3) / 1e6, "unit": UNIT,
+            "device_ms": t_ms, "stage_ms": stage, "value": samples / (t_ms * 1e-3) / 1e6, "unit": UNIT,
             "algorithmic_bytes": comp + pcm, "hbm_gbs": (comp + pcm) / (t_ms * 1e-3) / 1e9,
             "parity": "device checksum of the resident PCM == checksum of the encoder's input"}
 

@@ -9,6 +9,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${tag}_
 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --batch-tracks 0 > gpurun_out/plain_${tag}.json 2> gpurun_out/plain_${tag}.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --batch-tracks 0 > gpurun_out/ncu_${tag}.log 2>&1
 for k in k123_decode k12_entropy_lpc k3_stereo_pack; do
-ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 2 --launch-count 1 -f -o gpurun_out/prof_${tag}_$k python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --batch-tracks 0 > gpurun_out/ncu_${tag}_$k.log 2>&1
+skip=2; [ $k = k123_decode ] && skip=0      # the fully fused launch runs once (zero-copy parity pass)
+ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip $skip --launch-count 1 -f -o gpurun_out/prof_${tag}_$k python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --batch-tracks 0 > gpurun_out/ncu_${tag}_$k.log 2>&1
 done
 ls -la gpurun_out | tail -12
