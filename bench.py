@@ -252,7 +252,19 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"numa_node": None, "cpus": None}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at communicator creation; stdout carries exactly one
+        # JSON line, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         torch.cuda.synchronize()
@@ -383,7 +395,7 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "e2e": {"value": samples_all / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": int(comp_bytes + 4 * n_frames), "d2h_bytes_per_step": int(pcm_bytes),
+                    "h2d_bytes_per_step": int(comp_bytes + 4 * n_frames) * world, "d2h_bytes_per_step": int(pcm_bytes) * world,   # whole job
                     "ms_per_step": e2e_ms_max, "steps": args.e2e_steps,
                     "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"], "pipeline_ms": tm_e2e["kernels_ms"],
                     "api_ms": tm_e2e["total_ms"]},
