@@ -119,6 +119,7 @@ struct Device {
     std::vector<HostCopy> copies;         // the same bytes split at chunk boundaries
     std::vector<Chunk> chunks;
     uint32_t chunk_frames = 0;
+    bool chunk_taper = false;
     std::vector<cudaEvent_t> events;
     bool resident = false;            // arena bytes + K0 results are on the device
     bool decoded = false;             // kernels ran: per-frame status is valid
@@ -142,6 +143,7 @@ struct alacgpu_ctx {
     alacgpu_timing timing{};
     // stage timings of the last pipeline are read back from its CUDA events on demand (alacgpu_get_timing):
     // ~80 event queries are not on the caller's critical path
+    bool index_stale = false;             // alacgpu_reindex: K0 runs again inside the next decode_all
     bool timing_pending = false;
     bool tp_stage = false, tp_index = false, tp_decode = false, tp_d2h = false, tp_zc = false;
     std::string err;
@@ -355,16 +357,22 @@ int32_t build_plan(alacgpu_ctx *ctx)
 
 // Split the device's frames into chunks of `cf` frames and split the host->arena copies at
 // the chunk boundaries, so chunk c never waits for bytes of chunk c+1.
-void build_chunks(alacgpu_ctx *ctx, Device &d, uint32_t cf)
+// `taper`: the first chunks are smaller (cf/4, cf/2, 3cf/4): while chunks stream in from the host the
+// call ends at (first PCM ready) + (D2H of all PCM), so the first chunk should be on the GPU early.
+void build_chunks(alacgpu_ctx *ctx, Device &d, uint32_t cf, bool taper)
 {
-    if (d.chunk_frames == cf && !d.chunks.empty()) return;
+    if (d.chunk_frames == cf && d.chunk_taper == taper && !d.chunks.empty()) return;
     d.chunks.clear();
     d.copies.clear();
+    d.chunk_taper = taper;
     const uint64_t n_local = d.f_hi - d.f_lo;
-    for (uint64_t f0 = 0; f0 < n_local; f0 += cf) {
+    uint32_t step = cf;
+    for (uint64_t f0 = 0; f0 < n_local; f0 += step) {
+        step = cf;
+        if (taper && d.chunks.size() < 3) step = std::max<uint32_t>(64u, ((cf * (uint32_t)(d.chunks.size() + 1) / 4u) + 31u) & ~31u);
         Chunk c{};
         c.f0 = f0;
-        c.n = (uint32_t)std::min<uint64_t>(cf, n_local - f0);
+        c.n = (uint32_t)std::min<uint64_t>(step, n_local - f0);
         c.copy_lo = (uint32_t)d.copies.size();
         uint64_t f = f0;
         while (f < f0 + c.n) {                      // runs of frames of one track inside the chunk
@@ -397,7 +405,7 @@ constexpr size_t kEvBase = 4;       // [0] pipeline start, [1] pipeline end, [2]
 
 // Issue one chunk's kernels on its slot stream.
 int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool with_k0, bool with_decode,
-                    size_t ev, uint32_t *launches, uint8_t *pcm_override, bool streaming)
+                    size_t ev, uint32_t *launches, uint8_t *pcm_override, bool streaming, bool early = false)
 {
     ChunkArgs ca{};
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
@@ -411,8 +419,10 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
         // the first PCM should leave as early as possible: both channels (end to end 9.9 -> 9.65 ms).
         static const int q_last = getenv("ALACGPU_QUAD_MIN_LAST") ? atoi(getenv("ALACGPU_QUAD_MIN_LAST")) : 17;
         static const int q_first = getenv("ALACGPU_QUAD_MIN_FIRST") ? atoi(getenv("ALACGPU_QUAD_MIN_FIRST")) : -1;
-        const int qf = q_first >= 0 ? q_first : (streaming ? 17 : 0);
-        ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC)) ? ((q_last & 255) | ((qf & 255) << 8)) : 0;
+        static const int q_early = getenv("ALACGPU_QUAD_MIN_EARLY") ? atoi(getenv("ALACGPU_QUAD_MIN_EARLY")) : 0;
+        int ql = q_last, qf = q_first >= 0 ? q_first : (streaming ? 17 : 0);
+        if (early && q_early > 0) ql = qf = q_early;          // the first chunks of a streamed call run on an idle GPU
+        ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC)) ? ((ql & 255) | ((qf & 255) << 8)) : 0;
     }
     const size_t cf2 = 2u * (size_t)d.chunk_frames;
     ca.progress = s.progress.p;
@@ -553,7 +563,8 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (!n_local) continue;
         CU(cudaSetDevice(d.id));
         const uint32_t cf = chunk_frames_for(d);
-        build_chunks(ctx, d, cf);
+        static const bool no_taper = getenv("ALACGPU_NO_TAPER") != nullptr;
+        build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper);
         const size_t n_chunks = d.chunks.size();
         const int slots_used = (int)std::min<size_t>(kSlots, n_chunks);
         if (decode)
@@ -580,7 +591,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
                 CU(cudaEventRecord(d.events[ev + 5], d.st_h2d));
                 CU(cudaStreamWaitEvent(s.st, d.events[ev + 5], 0));
             }
-            int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &launches, zc, stage);
+            int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &launches, zc, stage, stage && ci < 3);
             if (r) return r;
             if (pcm_dst && !zc && decode && c.pcm_hi > c.pcm_lo) {
                 CU(cudaStreamWaitEvent(d.st_d2h, d.events[ev + 4], 0));
@@ -867,13 +878,11 @@ int32_t alacgpu_reindex(alacgpu_ctx *ctx)
     if (!ctx) return ALACGPU_ERR_INVALID_ARG;
     int32_t r = alacgpu_prepare(ctx, nullptr);
     if (r) return r;
-    const double t0 = now_ms();
-    ctx->timing = alacgpu_timing{};
-    r = run_pipeline(ctx, false, true, false, nullptr, &ctx->index_launches);
-    fill_totals(ctx);
-    ctx->timing.kernel_launches = ctx->index_launches;
-    ctx->timing.total_ms = (float)(now_ms() - t0);
-    return r;
+    // lazy: the next decode_all runs K0 over the resident bytes inside its own pipeline (one launch
+    // sequence, one synchronisation per step instead of three)
+    ctx->index_stale = true;
+    for (Device &d : ctx->devs) { d.decoded = false; d.pcm_resident = false; }
+    return ALACGPU_OK;
 }
 
 int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uint64_t *track_pcm_off,
@@ -886,11 +895,14 @@ int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uin
     if (r) return r;
     if (getenv("ALACGPU_HOST_TIMING")) fprintf(stderr, "[alacgpu] build_plan %.3f ms\n", now_ms() - t0);
     const bool resident = all_resident(ctx);
-    if (!resident) { ctx->timing = alacgpu_timing{}; ctx->index_launches = 0; }
-    // not yet staged: stream mdat in, index and decode chunk by chunk; else decode only
+    const bool reindex = !resident || ctx->index_stale;
+    if (reindex) { finish_timing(ctx); ctx->timing = alacgpu_timing{}; ctx->index_launches = 0; }
+    // not yet staged: stream mdat in, index and decode chunk by chunk; else decode only (after
+    // alacgpu_reindex: header pre-pass + decode over the resident bytes)
     uint32_t launches = 0;
-    r = run_pipeline(ctx, !resident, !resident, true, pcm_dst, &launches);
+    r = run_pipeline(ctx, !resident, reindex, true, pcm_dst, &launches);
     if (r) return r;
+    ctx->index_stale = false;
     fill_totals(ctx);
     ctx->timing.kernel_launches = ctx->index_launches + launches;
     ctx->timing.total_ms = (float)(now_ms() - t0);

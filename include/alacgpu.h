@@ -189,9 +189,11 @@ ALACGPU_API int32_t alacgpu_total_pcm_bytes(alacgpu_ctx *ctx, uint64_t *total_pc
  * chunk by chunk, overlapped with the kernels and the PCM copies. */
 ALACGPU_API int32_t alacgpu_prepare(alacgpu_ctx *ctx, uint64_t *total_pcm_bytes);
 
-/* Re-run only the device side of alacgpu_prepare (the header pre-pass) over the
- * bytes already resident in HBM; no host->device copy.  Used to time the whole
- * kernel path with resident inputs. */
+/* Mark the device-side frame index stale: the next alacgpu_decode_all re-runs
+ * the header pre-pass (K0) over the bytes already resident in HBM inside its
+ * own pipeline, before the decode kernels; no host->device copy.  (Stages the
+ * tracks first if they are not resident yet.)  Used to time the whole kernel
+ * path with resident inputs. */
 ALACGPU_API int32_t alacgpu_reindex(alacgpu_ctx *ctx);
 
 /* Decode every frame of every track.  pcm_dst: caller-owned HOST buffer of

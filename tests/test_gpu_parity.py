@@ -307,6 +307,20 @@ def test_two_devices_in_one_context(gen, oracle):
         assert dec.read_frame(1, f) == got[1][len(got[1]) - tracks[1].frame_samples[f] * 6:]
 
 
+@pytest.mark.parametrize("env", [
+    {"ALACGPU_QUAD_MIN_LAST": "3", "ALACGPU_QUAD_MIN_FIRST": "3"},      # four-lane LPC for (almost) every stream: T = 2..8
+    {"ALACGPU_QUAD_MIN_LAST": "9", "ALACGPU_QUAD_MIN_FIRST": "13"},
+    {"ALACGPU_QUAD_MIN_LAST": "0", "ALACGPU_QUAD_MIN_FIRST": "0", "ALACGPU_NO_TAPER": "1"},   # one lane per stream only
+])
+def test_tuning_environment_does_not_change_bytes(env):
+    """The four-lane LPC thresholds and the chunk taper are per-process environment knobs."""
+    import os, subprocess, sys
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_env_case.py")], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "env case ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_random_payload_fuzz_matches_oracle(seed, gen, oracle):
     """valid headers + random payload bits (tests/test_fuzz_oracle_model.py): PCM and status words of

@@ -23,4 +23,5 @@ for it in range(4):
     dec.decode_all(out, want_status=False)
     t3 = time.perf_counter()
     print(f"step {it}: clear {1e3*(t1-t0):.2f} add_track {1e3*(t2-t1):.2f} decode_all {1e3*(t3-t2):.2f} ms", flush=True)
+dec.timing()
 assert out.array[:len(tr.pcm)].tobytes() == tr.pcm
