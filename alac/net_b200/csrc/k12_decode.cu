@@ -14,8 +14,8 @@
 // behind it) instead of the sum.
 //
 // Hand-off: per stream one 32-bit progress word in global memory.  The entropy
-// lane stores a row block, and every 32 residuals fences and publishes the
-// count (kStreamDone at the end of the channel, also after a decode fault); the
+// lane stores its residuals one by one, and every 64 steps fences and publishes its
+// output index (kStreamDone at the end of the channel, also after a decode fault); the
 // LPC lane checks the word (ld.acquire.gpu) before it prefetches a residual
 // block it has not been granted yet, and reads the plane with ld.global.cg.
 // Forward progress: an LPC block only ever waits on entropy blocks, which have
