@@ -415,8 +415,10 @@ def run_ours(args):
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             v, sample, _ = cpu_decode_rate(tracks, max(8, min(2048, tracks[0].n_frames // cores)), cores, repeats=2)
+            v1, _, _ = cpu_decode_rate(tracks, 256, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": sample + "; oracle/ C restatement (C# reference not runnable here)"}
+                                    "sample": sample + "; oracle/ C restatement (C# reference not runnable here)",
+                                    "one_core_value": v1}
         print(json.dumps(line), flush=True)
     dec.close()
     if world > 1:
