@@ -184,6 +184,8 @@ static uint32_t quad_warp_bound(const ChunkArgs &a)
     return (a.n * per_frame + 7u) / 8u;
 }
 
+constexpr uint32_t kSmallChunkFrames = 20480;    // up to here a chunk is latency-bound (runtime.cu: kFullFusionMaxFrames)
+
 static int lanes_log2_of(int lanes_per_warp)
 {
     if (lanes_per_warp == 16) return 4;
@@ -215,7 +217,7 @@ cudaError_t launch_k2(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
     // upper bound; warps past the work lists exit at once
-    const uint32_t warps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + quad_warp_bound(a);
+    const uint32_t warps = ((a.n * 2u + 31u) / 32u + 31u) + quad_warp_bound(a);
     k2_lpc<<<(warps + 3) / 4, kK2Threads, 0, st>>>(a);
     if (launches) *launches += 1;
     return cudaGetLastError();
@@ -227,7 +229,7 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + quad_warp_bound(a);
+    const uint32_t lwarps = ((a.n * 2u + 31u) / 32u + 31u) + quad_warp_bound(a);
     if (cudaError_t e = clear_planes(a, st)) return e;
     const uint32_t grid = eblocks + (lwarps + 3) / 4;
     static const char *trace_path = getenv("ALACGPU_TRACE");
@@ -237,7 +239,20 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
         cudaMemset(tr, 0, (size_t)grid * 12 * sizeof(unsigned long long));
         cudaMemcpyToSymbol(g_trace, &tr, sizeof(tr));
     }
-    k12_entropy_lpc<<<grid, kK1Threads, 0, st>>>(a, lg, eblocks);
+    // Blocks per SM.  The fused kernel needs 122 registers and 33 KB of shared memory, so four blocks fit
+    // an SM.  A small (latency-bound) chunk wants all its warps resident at once (configs[1]: 2.66 ms with
+    // four blocks, 2.97 ms with two).  A big chunk fills the machine anyway, and there fewer resident
+    // blocks are FASTER (configs[3]-shaped batch: 62.8 Gsamples/s with two blocks per SM, 57.3 with four:
+    // with two warps per scheduler the role loops stay in the instruction caches), so big chunks ask for
+    // 44 KB of unused dynamic shared memory.
+    static const int pad_env = getenv("ALACGPU_SMEM_PAD") ? atoi(getenv("ALACGPU_SMEM_PAD")) : -1;
+    const int pad_kb = pad_env >= 0 ? pad_env : (a.n > kSmallChunkFrames ? 44 : 0);
+    static bool attr_set = false;
+    if (pad_kb > 14 && !attr_set) {
+        cudaFuncSetAttribute(k12_entropy_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    k12_entropy_lpc<<<grid, kK1Threads, (size_t)pad_kb * 1024, st>>>(a, lg, eblocks);
     if (tr) {
         cudaStreamSynchronize(st);
         std::vector<unsigned long long> h((size_t)grid * 12);
@@ -263,7 +278,7 @@ cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st,
     const int lg = lanes_log2_of(lanes_per_warp);
     const uint32_t ewarps = (a.n + (1u << lg) - 1) >> lg;
     const uint32_t eblocks = (ewarps + 3) / 4;
-    const uint32_t lwarps = (a.n * 2u + ALACGPU_LPC_STREAMS_PER_WARP - 1u) / ALACGPU_LPC_STREAMS_PER_WARP + quad_warp_bound(a);
+    const uint32_t lwarps = ((a.n * 2u + 31u) / 32u + 31u) + quad_warp_bound(a);
     const uint32_t lblocks = (lwarps + 3) / 4;
     // pack blocks: one per ~2400 tasks (a task is ~2.5 us of one warp, the decode stages leave ~2.5 ms)
     const uint32_t tasks = ((a.max_sf + kPackGroup - 1) / kPackGroup) * a.n;

@@ -7,25 +7,22 @@
 // (frame, channel) "stream".  One LANE owns one stream and walks its own row
 // of the plane four samples at a time (one 16-byte load and one 16-byte store
 // per four samples, prefetched two blocks ahead).  The work per sample is
-// proportional to the stream's predictor order, and all lanes of a warp
-// execute the warp's largest order, so a pre-pass (k0s_order_sort) sorts the
-// chunk's active streams by DESCENDING order: warps are homogeneous, and the
-// heaviest warps are scheduled first (one warp per block, blocks issued in
-// order), which is what bounds the makespan when a batch has fewer streams
-// than the GPU has lanes.
+// proportional to the stream's predictor order, so a pre-pass (k0s_order_sort)
+// sorts the chunk's active streams by DESCENDING order and pads every order
+// class to whole warps: a warp never mixes orders, each warp runs the code for
+// exactly its order (template on the tap count, tap weights as immediates),
+// and the heaviest warps are scheduled first (blocks are issued in order),
+// which is what bounds the makespan when a batch has fewer streams than the
+// GPU has lanes.
 //
 // The per-sample body is STRAIGHT-LINE code, identical for every lane:
 //   * coefficients c[M] and the last M+1 outputs H[M+1] live in registers,
-//     statically indexed, fully unrolled over the taps; M is the smallest
-//     bucket >= the largest order among the warp's lanes;
-//   * a lane whose order is below M keeps H[j] == base for every j > order
-//     (a masked shift), so its surplus taps see a zero difference and drop
-//     out of the dot product AND of the adaptation without any predicate;
+//     statically indexed, fully unrolled over the taps;
 //   * the data-dependent early exit of the coefficient update
 //     (AlacFile.cs:322) is the predicate "running error still positive" on a
 //     sign-normalised error E = sign(err) * err;
-//   * warm-up samples, delta mode (order 31) and zero residuals run the same
-//     code with E = 0 and a select on the output.
+//   * warm-up samples and zero residuals run the same code with E = 0 and a
+//     select on the output; delta mode (order 31, :268-282) is its own class.
 #pragma once
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
@@ -61,13 +58,18 @@ __device__ __forceinline__ bool lpc_quad(const FrameDesc &d, int ch, int key, in
     return thr != 0 && key >= thr;
 }
 
-// perm[0 .. n_rest): one-lane streams, heaviest first; perm[2n .. 2n + n_quad): four-lane streams,
-// heaviest first; perm_count[0] = n_rest, perm_count[1] = n_quad.
+// perm[0 .. n_rest): one-lane streams, heaviest order first, every order class padded with kNoStream to a
+// multiple of 32 (a warp never mixes orders); perm[quad_base(n) .. + n_quad): four-lane streams, heaviest
+// first; perm_count[0] = n_rest (padded), perm_count[1] = n_quad.
+constexpr uint32_t kPermPad = 32u * 32u;            // room for the padding of the 31 one-lane classes
+__host__ __device__ __forceinline__ uint32_t quad_base(uint32_t n_frames) { return 2u * n_frames + kPermPad; }
+constexpr uint32_t kNoStream = 0xFFFFFFFFu;
+
 __global__ void __launch_bounds__(kSortThreads)
 k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *__restrict__ perm,
                uint32_t *__restrict__ perm_count, uint8_t *__restrict__ lpc_flag, const int use_quads)
 {
-    __shared__ uint32_t hist[64], cursor[64];
+    __shared__ uint32_t hist[64], cursor[64], padded;
     if (threadIdx.x < 64) hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t n_streams = n_frames * 2u;
@@ -79,13 +81,15 @@ k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int key = 30; key >= 0; --key) { cursor[key] = acc; acc += hist[key]; }
+        for (int key = 30; key >= 0; --key) { cursor[key] = acc; acc += (hist[key] + 31u) & ~31u; }
         cursor[31] = 0;
-        perm_count[0] = acc;
+        perm_count[0] = padded = acc;
         acc = 0;
-        for (int key = 30; key >= 0; --key) { cursor[32 + key] = n_streams + acc; acc += hist[32 + key]; }
+        for (int key = 30; key >= 0; --key) { cursor[32 + key] = quad_base(n_frames) + acc; acc += hist[32 + key]; }
         perm_count[1] = acc;
     }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < padded; k += kSortThreads) perm[k] = kNoStream;
     __syncthreads();
     for (uint32_t s = threadIdx.x; s < n_streams; s += kSortThreads) {
         const FrameDesc d = desc[s >> 1];
@@ -122,15 +126,42 @@ __device__ __forceinline__ void lpc_tap(int32_t &c, int32_t &E, uint32_t &acc, c
         : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "r"(negm));
 }
 
+// the same with the weight -(order - p) as an immediate (one-lane warps are homogeneous in order)
+template <int NEGM>
+__device__ __forceinline__ void lpc_tap_imm(int32_t &c, int32_t &E, uint32_t &acc, const int32_t h, const int32_t nsg,
+                                            const int32_t sgbase, const uint32_t r, const uint32_t q)
+{
+    asm("{\n\t"
+        ".reg .s32 dp, a, u, t;\n\t"
+        ".reg .pred act;\n\t"
+        "mad.lo.s32 dp, %3, %4, %5;\n\t"
+        "setp.gt.s32 act, %1, 0;\n\t"
+        "mad.lo.s32 %2, %0, dp, %2;\n\t"
+        "abs.s32 a, dp;\n\t"
+        "max.s32 t, dp, -1;\n\t"
+        "add.s32 a, a, %6;\n\t"
+        "min.s32 t, t, 1;\n\t"
+        "shr.u32 u, a, %7;\n\t"
+        "@act sub.s32 %0, %0, t;\n\t"
+        "@act mad.lo.s32 %1, u, %8, %1;\n\t"
+        "}"
+        : "+r"(c), "+r"(E), "+r"(acc)
+        : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "n"(NEGM));
+}
+// taps pp = P .. 0 of an order-M stream (AlacFile.cs:322: newest coefficient index first)
+template <int M, int P>
+__device__ __forceinline__ void lpc_taps(int32_t (&c)[M], const int32_t (&H)[M + 1], int32_t &E, uint32_t &acc, const int32_t nsg,
+                                         const int32_t sgbase, const uint32_t r, const uint32_t q)
+{
+    lpc_tap_imm<P - M>(c[P], E, acc, H[P], nsg, sgbase, r, q);
+    if constexpr (P > 0) lpc_taps<M, P - 1>(c, H, E, acc, nsg, sgbase, r, q);
+}
+
 #ifndef ALACGPU_LPC_STREAMS_PER_WARP
 #define ALACGPU_LPC_STREAMS_PER_WARP 32
 #endif
 constexpr int kK2Threads = 128;    // four LPC warps per block; blocks are issued heaviest first
 
-// All 32 lanes run this; `active` gates memory traffic only.
-//   row    : the lane's row of the plane (16-byte aligned), n samples (0 if inactive)
-//   nmax   : warp maximum of n
-//   ord    : 1..30 general, 31 delta mode (AlacFile.cs:268-282); inactive lanes pass 31
 __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
 {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -169,28 +200,20 @@ __device__ __forceinline__ void wait_avail(const uint32_t *prog, const uint32_t 
     }
 }
 
+// All 32 lanes run this; `active` gates memory traffic only.  Every active lane's order is exactly M
+// (1..30).
+//   row    : the lane's row of the plane (16-byte aligned), n samples (0 if inactive)
+//   nmax   : warp maximum of n
 template <int M, bool kPoll, bool kPublish>
-__device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int ord,
-                                      const int q, const int16_t *__restrict__ coef16, const bool active,
-                                      int32_t *hist /* this lane's column of a [32][32] shared ring */,
+__device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax, const int rss, const int q,
+                                      const int16_t *__restrict__ coef16, const bool active,
                                       const uint32_t *prog, uint32_t *done)
 {
-    const bool delta = ord == 31;
-    const int ordm = delta ? 0 : ord;              // taps this lane really has
-    int32_t c[M], negm[M], H[M + 1];
-    uint32_t msk[M + 1];
+    int32_t c[M], H[M + 1];                        // H[j] = o[i-1-j]; H[M] is the base o[i-1-M]
 #pragma unroll
-    for (int j = 0; j < M; j++) {
-        c[j] = (active && j < ordm) ? (int32_t)coef16[j] : 0;
-        negm[j] = j - ordm;                        // -(order - p), AlacFile.cs:329
-        asm volatile("" : "+r"(negm[j]));          // keep as a register operand of the IMAD
-    }
+    for (int j = 0; j < M; j++) c[j] = active ? (int32_t)coef16[j] : 0;
 #pragma unroll
-    for (int j = 0; j <= M; j++) {
-        msk[j] = (uint32_t)((ordm - j) >> 31);     // all ones iff j > order
-        asm volatile("" : "+r"(msk[j]));           // keep as data: the shift below is one LOP3 per tap
-        H[j] = 0;
-    }
+    for (int j = 0; j <= M; j++) H[j] = 0;
 
     const int32_t rnd = (int32_t)(1u << ((q - 1) & 31));            // :306 (quant 0 -> 1 << 31)
     // sign * ((val*sign) >> quant) = (|val| + r) >> quant with r = 0 for a positive error and
@@ -207,12 +230,11 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
     int4 cur = active ? __ldcg(row4) : make_int4(0, 0, 0, 0);
     int4 nx1 = (active && nblk > 1) ? __ldcg(row4 + 1) : make_int4(0, 0, 0, 0);
     H[0] = cur.x;                                                   // first sample always copies (:259-260)
-    hist[0] = H[0];
     for (int b = 0; b < nblk_max; b++) {
         // every 8 blocks: make sure the 32 residuals after the ones already granted are there
         if (kPoll && (b & 7) == 7) wait_avail(prog, (uint32_t)min(nblk, b + 11) * 4u, avail, active, stalled);
         const int4 nx2 = (active && b + 2 < nblk) ? __ldcg(row4 + b + 2) : make_int4(0, 0, 0, 0);
-        // The four samples of a block run through ONE copy of the tap code (the body is ~10 M
+        // The four samples of a block run through ONE copy of the tap code (the body is ~11 M
         // instructions; unrolling it four times would overflow the instruction cache), so the
         // block's residuals / outputs are moved with selects instead of static indices.
         int32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
@@ -220,33 +242,24 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
         for (int u = 0; u < 4; u++) {
             const int i = b * 4 + u;
             const int32_t e = u == 0 ? cur.x : (u == 1 ? cur.y : (u == 2 ? cur.z : cur.w));
-            int32_t o;
-            if (i == 0) {
-                o = H[0];
-            } else {
-                // base of the NEXT sample, o[i - ord] (ord >= 1): from the lane's ring of its last 32
-                // outputs in shared memory ([slot][lane]: bank == lane, conflict free)
-                const int32_t nb = hist[((uint32_t)(i - ord) & 31u) * 32];
-                const bool main = !delta && i > ord;                        // warm-up covers i = 1..ord (:284-293)
-                const int32_t base = H[M];                                  // o[i-1-ord]
+            int32_t o = H[0];
+            if (i != 0) {
+                const bool main = i > M;                                    // warm-up covers i = 1..M (:284-293)
+                const int32_t base = H[M];                                  // o[i-1-M]
                 const int32_t nsg = e < 0 ? 1 : -1;                         // -sign(err)
                 const int32_t sgbase = e < 0 ? (int32_t)(0u - (uint32_t)base) : base;
                 int32_t E = main ? (e < 0 ? (int32_t)(0u - (uint32_t)e) : e) : 0;   // sign(err) * err
                 const uint32_t r = e < 0 ? rneg : 0u;
                 uint32_t acc = 0;
-#pragma unroll
-                for (int pp = M - 1; pp >= 0; --pp)
-                    lpc_tap(c[pp], E, acc, H[pp], nsg, sgbase, r, (uint32_t)q, negm[pp]);
+                lpc_taps<M, M - 1>(c, H, E, acc, nsg, sgbase, r, (uint32_t)q);
                 const int32_t sum = (int32_t)(acc * (uint32_t)nsg);         // sum of (buf[b+order-j]-buf[b])*coef[j]
                 int32_t v = (int32_t)((uint32_t)rnd + (uint32_t)sum) >> q;  // :306-307
                 v = (int32_t)((uint32_t)v + (uint32_t)base + (uint32_t)e);  // :308
-                const int32_t w = (int32_t)((uint32_t)H[0] + (uint32_t)e);  // warm-up / delta (:279, :288)
+                const int32_t w = (int32_t)((uint32_t)H[0] + (uint32_t)e);  // warm-up (:288)
                 const int32_t x = main ? v : w;
                 o = (int32_t)((uint32_t)x << sh) >> sh;                     // :309-310
-                hist[((uint32_t)i & 31u) * 32] = o;
-                // masked shift: true history up to the lane's order, the new base beyond it
 #pragma unroll
-                for (int j = M; j > 0; --j) H[j] = (int32_t)(((uint32_t)nb & msk[j]) | ((uint32_t)H[j - 1] & ~msk[j]));
+                for (int j = M; j > 0; --j) H[j] = H[j - 1];
                 H[0] = o;
             }
             o0 = u == 0 ? o : o0; o1 = u == 1 ? o : o1; o2 = u == 2 ? o : o2; o3 = u == 3 ? o : o3;
@@ -258,6 +271,38 @@ __device__ __noinline__ bool lpc_warp(int32_t *row, const int n, const int nmax,
         }
         cur = nx1;
         nx1 = nx2;
+    }
+    if (kPublish) {
+        __threadfence();
+        if (active) st_relaxed(done, 0xFFFFFFFFu);
+    }
+    return stalled;
+}
+
+// Delta mode (order 31, AlacFile.cs:268-282): o[i] = o[i-1] + e[i], no taps.
+template <bool kPoll, bool kPublish>
+__device__ __noinline__ bool lpc_delta(int32_t *row, const int n, const int nmax, const int rss, const bool active,
+                                       const uint32_t *prog, uint32_t *done)
+{
+    const int sh = (32 - rss) & 31;
+    int4 *row4 = reinterpret_cast<int4 *>(row);
+    const int nblk = (n + 3) >> 2, nblk_max = (nmax + 3) >> 2;
+    uint32_t avail = kPoll ? 0u : 0xFFFFFFFFu;
+    bool stalled = false;
+    int32_t prev = 0;
+    for (int b = 0; b < nblk_max; b++) {
+        if (kPoll && (b & 7) == 0) wait_avail(prog, (uint32_t)min(nblk, b + 8) * 4u, avail, active, stalled);
+        int4 v = (active && b < nblk) ? __ldcg(row4 + b) : make_int4(0, 0, 0, 0);
+        if (b == 0) prev = v.x;
+        else prev = v.x = (int32_t)((uint32_t)(prev + v.x) << sh) >> sh;
+        prev = v.y = (int32_t)((uint32_t)(prev + v.y) << sh) >> sh;
+        prev = v.z = (int32_t)((uint32_t)(prev + v.z) << sh) >> sh;
+        prev = v.w = (int32_t)((uint32_t)(prev + v.w) << sh) >> sh;
+        if (active && b < nblk) row4[b] = v;
+        if (kPublish && (b & 7) == 7) {
+            __threadfence();
+            if (active && b < nblk) st_relaxed(done, (uint32_t)(b + 1) * 4u);
+        }
     }
     if (kPublish) {
         __threadfence();
@@ -385,7 +430,8 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
 }
 
 // One LPC warp.  The first ceil(n_quad / 8) warps take the four-lane streams (eight per warp), the
-// others 32 one-lane streams each.  hist_warp: this warp's 4 KB of shared memory.
+// others 32 one-lane streams of ONE order each.  hist_warp: this warp's 4 KB of shared memory (the
+// four-lane warps' output rings).
 template <bool kPoll, bool kPublish>
 __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int32_t *hist_warp)
 {
@@ -394,18 +440,18 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
     const uint32_t quad_warps = (n_quad + 7u) / 8u;
     const bool quad = warp < quad_warps;
     if (!quad) warp -= quad_warps;
-    constexpr uint32_t SPW = ALACGPU_LPC_STREAMS_PER_WARP;
-    const uint32_t idx = quad ? warp * 8u + (uint32_t)(lane >> 2) : warp * SPW + (uint32_t)lane;
-    if (!quad && warp * SPW >= n_active) return;
-    const bool active = quad ? idx < n_quad : (idx < n_active && (uint32_t)lane < SPW);
-    int n = 0, rss = 32, ord = 31, q = 0;
+    const uint32_t idx = quad ? warp * 8u + (uint32_t)(lane >> 2) : warp * 32u + (uint32_t)lane;
+    if (!quad && warp * 32u >= n_active) return;
+    uint32_t sid = kNoStream;
+    if (quad ? idx < n_quad : idx < n_active) sid = quad ? a.perm[quad_base(a.n) + idx] : a.perm[idx];
+    const bool active = sid != kNoStream;
+    int n = 0, rss = 32, ord = 0, q = 0;
     const int16_t *coef16 = nullptr;
     int32_t *row = nullptr;
     const uint32_t *prog = nullptr;
     uint32_t *done = nullptr;
     uint64_t f = 0;
     if (active) {
-        const uint32_t sid = quad ? a.perm[2u * a.n + idx] : a.perm[idx];
         f = a.f0 + (sid >> 1);
         const int ch = (int)(sid & 1u);
         const FrameDesc d = a.desc[f];
@@ -415,11 +461,9 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
         prog = a.progress + sid;
         done = a.lpc_done + sid;
     }
-    // taps needed by this warp: delta mode (31) needs none
-    const int need = active ? (ord == 31 ? 1 : ord) : 0;
-    const int maxo = __reduce_max_sync(0xffffffffu, need);
+    const int maxo = __reduce_max_sync(0xffffffffu, ord);      // one-lane warps: THE order of the warp (31 = delta mode)
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    bool stalled;
+    bool stalled = false;
     if (quad) {
         int32_t *ring = hist_warp + (lane >> 2);
         if (!active) ord = 1;
@@ -435,23 +479,16 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
         if (kPoll && active && stalled && (lane & 3) == 0) a.desc[f].status = FS_INTERNAL;
         return;
     }
-    int32_t *hist = hist_warp + lane;
-#define ALACGPU_LPC(MM) stalled = lpc_warp<MM, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, hist, prog, done)
-    if (maxo <= 2) ALACGPU_LPC(2);
-    else if (maxo <= 4) ALACGPU_LPC(4);
-    else if (maxo <= 6) ALACGPU_LPC(6);
-    else if (maxo <= 8) ALACGPU_LPC(8);
-    else if (maxo <= 10) ALACGPU_LPC(10);
-    else if (maxo <= 12) ALACGPU_LPC(12);
-    else if (maxo <= 14) ALACGPU_LPC(14);
-    else if (maxo <= 16) ALACGPU_LPC(16);
-    else if (maxo <= 18) ALACGPU_LPC(18);
-    else if (maxo <= 20) ALACGPU_LPC(20);
-    else if (maxo <= 22) ALACGPU_LPC(22);
-    else if (maxo <= 24) ALACGPU_LPC(24);
-    else if (maxo <= 26) ALACGPU_LPC(26);
-    else if (maxo <= 28) ALACGPU_LPC(28);
-    else ALACGPU_LPC(30);
+#define ALACGPU_LPC(MM) case MM: stalled = lpc_warp<MM, kPoll, kPublish>(row, n, nmax, rss, q, coef16, active, prog, done); break
+    switch (maxo) {
+        ALACGPU_LPC(1); ALACGPU_LPC(2); ALACGPU_LPC(3); ALACGPU_LPC(4); ALACGPU_LPC(5); ALACGPU_LPC(6);
+        ALACGPU_LPC(7); ALACGPU_LPC(8); ALACGPU_LPC(9); ALACGPU_LPC(10); ALACGPU_LPC(11); ALACGPU_LPC(12);
+        ALACGPU_LPC(13); ALACGPU_LPC(14); ALACGPU_LPC(15); ALACGPU_LPC(16); ALACGPU_LPC(17); ALACGPU_LPC(18);
+        ALACGPU_LPC(19); ALACGPU_LPC(20); ALACGPU_LPC(21); ALACGPU_LPC(22); ALACGPU_LPC(23); ALACGPU_LPC(24);
+        ALACGPU_LPC(25); ALACGPU_LPC(26); ALACGPU_LPC(27); ALACGPU_LPC(28); ALACGPU_LPC(29); ALACGPU_LPC(30);
+        case 31: stalled = lpc_delta<kPoll, kPublish>(row, n, nmax, rss, active, prog, done); break;
+        default: break;
+    }
 #undef ALACGPU_LPC
     if (kPoll && active && stalled) a.desc[f].status = FS_INTERNAL;   // never expected: see wait_avail
 }

@@ -411,7 +411,7 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
     ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
-    ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames;
+    ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames + 1024u;
     {
         // four-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
         // streams from order 17 up (measured best on configs[1]: 2.72 ms; both channels 3.1 ms -- the extra
@@ -570,7 +570,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (decode)
             for (int s = 0; s < slots_used; s++) {
                 CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
-                CU(d.slots[s].perm.reserve((size_t)cf * 4u + 4u));
+                CU(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
                 CU(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
             }
         get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
