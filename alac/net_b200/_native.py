@@ -21,6 +21,8 @@ FLAG_KEEP_DEVICE_PCM = 0x1
 FLAG_NO_FUSION = 0x2
 FLAG_NO_PACK_FUSION = 0x4
 FLAG_NO_ZERO_COPY = 0x8
+FLAG_NO_QUAD_LPC = 0x10
+FLAG_FORCE_PACK_FUSION = 0x20
 
 # every symbol include/alacgpu.h declares (tests check the export table against this)
 EXPORTS = [

@@ -24,6 +24,14 @@ namespace ALACdotNET.Decoder.Gpu
         BadRss = 5, History = 6, RunOverflow = 7, Order0Long = 8, Internal = 9
     }
 
+    /// <summary>alacgpu_opts.flags (ALACGPU_FLAG_* in alacgpu.h); every combination yields the same bytes.</summary>
+    [Flags]
+    internal enum AlacGpuFlags : uint
+    {
+        None = 0, KeepDevicePcm = 0x1, NoFusion = 0x2, NoPackFusion = 0x4, NoZeroCopy = 0x8,
+        NoQuadLpc = 0x10, ForcePackFusion = 0x20
+    }
+
     [StructLayout(LayoutKind.Sequential)]
     internal struct AlacGpuOpts
     {
