@@ -766,9 +766,9 @@ static int32_t add_track_impl(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, co
     if (cfg->max_samples_per_frame < 1 || cfg->max_samples_per_frame > kMaxFrameSamples ||
         cfg->max_samples_per_frame * bpsf > kMaxFramePcmBytes)
         return fail(ctx, ALACGPU_ERR_UNSUPPORTED, "max_samples_per_frame outside the reference's buffers (AlacFile.cs:28, AlacContext.cs:218)");
-    if (cfg->rice_kmodifier < 1 || cfg->rice_kmodifier > 31 || cfg->rice_history_mult < 0 || cfg->rice_history_mult > 255 ||
+    if (cfg->rice_kmodifier < 0 || cfg->rice_kmodifier > 31 || cfg->rice_history_mult < 0 || cfg->rice_history_mult > 255 ||
         cfg->rice_initial_history < 0 || cfg->rice_initial_history > 255)
-        return fail(ctx, ALACGPU_ERR_UNSUPPORTED, "rice parameters outside one cookie byte / kmodifier 1..31");
+        return fail(ctx, ALACGPU_ERR_UNSUPPORTED, "rice parameters outside one cookie byte / kmodifier 0..31");
     HostTrack t{};
     t.cfg = *cfg;
     t.mdat = mdat;
