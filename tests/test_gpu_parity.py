@@ -216,6 +216,22 @@ def test_kmodifier_and_history_cookie_variants(gen, oracle):
     assert (status[n_ok:] == 6).any()
 
 
+def test_extreme_frame_sizes(gen, oracle):
+    """maximum samples per frame (16384: AlacFile.cs:28; order 0 above 4096 samples is the reference's
+    Array.Copy fault, status 8) and frames of 1, 3 and 5 samples"""
+    rng = np.random.default_rng(7)
+    tracks = []
+    for ss, ch, msf in ((16, 2, 16384), (24, 2, 8192), (16, 1, 16384), (16, 2, 1), (16, 2, 3), (24, 1, 5)):
+        cfg = gen.TrackCfg(ss, ch, msf, 40, 10, 14, 44100)
+        n = msf * 3 + max(1, msf // 3)
+        x = gen.make_signal(int(rng.integers(1, 1 << 30)), n, ss, 44100, ch).copy()
+        fr = gen.make_frames(rng, cfg, n, ch == 2, orders=(0, 31), quants=(0, 15), rice_mods=(0, 7))
+        tracks.append(gen.build_track(cfg, x, fr))
+    for resident in (False, True):
+        got, status, _ = _decode(tracks, resident=resident)
+        _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
+
+
 def test_container_channel_mismatch(gen, oracle):
     """mono elements in a 2-channel container (zero-filled right) and stereo elements in a
     1-channel container (left only) -- AlacFile.cs:534-540, :353-354"""
