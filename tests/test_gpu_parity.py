@@ -232,6 +232,37 @@ def test_extreme_frame_sizes(gen, oracle):
         _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
 
 
+def test_degenerate_signals(gen, oracle):
+    """digital silence (one zero run spans the frame, run lengths above the 16-bit escape), full-scale noise
+    kept compressed (nearly every symbol takes the nine-ones escape), DC, full-scale alternation, sparse
+    impulses"""
+    rng = np.random.default_rng(11)
+    tracks = []
+    for name, ss, ch in (("silence", 16, 2), ("silence", 24, 1), ("noise", 16, 2), ("noise", 24, 2), ("dc", 16, 2),
+                         ("alt", 24, 2), ("sparse", 16, 1)):
+        cfg = gen.TrackCfg(ss, ch, 4096, 40, 10, 14, 44100)
+        n = 4096 * 4 + 777
+        lim = 1 << (ss - 1)
+        if name == "silence":
+            x = np.zeros((ch, n), dtype=np.int32)
+        elif name == "noise":
+            x = rng.integers(-lim, lim, size=(ch, n)).astype(np.int32)
+        elif name == "dc":
+            x = np.full((ch, n), lim - 1, dtype=np.int32)
+        elif name == "alt":
+            x = np.tile(np.array([lim - 1, -lim], dtype=np.int32), (ch, (n + 1) // 2))[:, :n].copy()
+        else:
+            x = np.zeros((ch, n), dtype=np.int32)
+            idx = rng.integers(0, n, size=40)
+            x[:, idx] = rng.integers(-lim, lim, size=(ch, 40))
+        fr = gen.make_frames(rng, cfg, n, ch == 2, orders=(0, 31), quants=(0, 15), rice_mods=(0, 7),
+                             auto_escape=name != "noise")
+        tracks.append(gen.build_track(cfg, x, fr))
+    for resident in (False, True):
+        got, status, _ = _decode(tracks, resident=resident)
+        _assert_tracks_equal(tracks, got, status, oracle)
+
+
 def test_container_channel_mismatch(gen, oracle):
     """mono elements in a 2-channel container (zero-filled right) and stereo elements in a
     1-channel container (left only) -- AlacFile.cs:534-540, :353-354"""
