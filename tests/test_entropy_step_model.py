@@ -63,7 +63,7 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask):
     steps = 0
     while i < nc:
         steps += 1
-        assert steps <= 2 * n + 4, "more steps than two per sample"
+        assert steps <= 4 * n, "at most four steps per sample: value and run length, each with its raw field"
         w = win.peek()
         ex = _exp_of(((w >> 23) ^ 0x1FF) | 0x4B000000)
         esc = ex == 0
@@ -127,10 +127,10 @@ CASES = [
     (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), loud=True, auto_escape=False)),
     (24, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(7, 7), loud=True, auto_escape=False)),
     (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), kmod=6, hist_mult=63, init_hist=200)),
-    (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), kmod=0)),
-    (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), kmod=1)),
+    (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), kmod=0, auto_escape=False)),
+    (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), kmod=1, auto_escape=False)),
     (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(4, 4), kmod=31, hist_mult=255, init_hist=255)),
-    (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(0, 7), hist_mult=3)),
+    (16, 2, dict(orders=(4, 8), quants=(9, 9), rice_mods=(0, 7), hist_mult=3, auto_escape=False)),
     (16, 1, dict(orders=(1, 4), quants=(9, 9), rice_mods=(4, 4), quiet=True)),
 ]
 
