@@ -176,7 +176,7 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 // Fused kernel only: block until the entropy lane that produces this stream has published at
 // least `need` residuals.  Bounded: a producer that never shows up (a bug, not a data
 // condition) flags the lane instead of hanging the GPU.
-constexpr uint32_t kSpinLimit = 1u << 22;   // x (256 ns sleep + one L2 round trip): seconds, i.e. only a genuine fault
+constexpr uint32_t kSpinLimit = 1u << 20;   // x (up to 4 us of back-off sleep + one L2 round trip): ~4 s, two orders of magnitude above any legitimate wait -- only a genuine fault
 // Warp-uniform on purpose: every lane polls its own stream's word, but the loop exit is a
 // warp vote, so the lanes leave together (a per-lane spin loop lets the warp fall apart and
 // run the tap code lane by lane afterwards).
