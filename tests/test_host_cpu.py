@@ -38,6 +38,20 @@ def test_header_symbols_are_exported(built):
     assert not stray, f"non-ABI symbols leak out of libalacgpu.so: {stray[:5]}"
 
 
+def test_csharp_binding_declares_every_symbol_and_flag():
+    """csharp/ cannot be compiled here (no dotnet): keep it in step with the header textually"""
+    cs = open(os.path.join(ROOT, "csharp", "AlacNet", "AlacGpuNative.cs")).read()
+    hdr = open(os.path.join(ROOT, "include", "alacgpu.h")).read()
+    dllimports = sorted(set(re.findall(r"extern\s+\w+\s+(alacgpu_\w+)\s*\(", cs)))
+    assert dllimports == _declared_symbols(), "P/Invoke declarations and header disagree"
+    flags = {int(v, 16) for v in re.findall(r"#define ALACGPU_FLAG_\w+ (0x[0-9a-fA-F]+)u", hdr)}
+    cs_flags = {int(v, 16) for v in re.findall(r"=\s*(0x[0-9a-fA-F]+)", cs[cs.index("enum AlacGpuFlags"):cs.index("struct AlacGpuOpts")])}
+    assert flags == cs_flags and len(flags) >= 6
+    frame_codes = {int(v) for v in re.findall(r"ALACGPU_FRAME_\w+ = (\d+)", hdr)}
+    cs_codes = {int(v) for v in re.findall(r"=\s*(\d+)", cs[cs.index("enum AlacGpuFrameStatus"):cs.index("enum AlacGpuFlags")])}
+    assert frame_codes == cs_codes
+
+
 def test_library_loads_and_answers_without_a_gpu(built):
     from alac.net_b200 import _native as N
     L = N.load()
