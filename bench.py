@@ -404,7 +404,8 @@ def run_ours(args):
                          "kernel": names[dom],
                          "scope": "dominant kernel: algorithmic bytes (compressed in + PCM out of the batch, "
                                   "intermediates not counted) / its average launch duration from CUDA events on "
-                                  "its launch stream; serial-dependency bound, see DESIGN.md section 3",
+                                  "its launch stream (the event pair also spans the work-list sort and the plane clear in "
+                                  "front of it, ~0.1 ms); serial-dependency / ALU-issue bound, see DESIGN.md section 3",
                          "dominant_kernel_ms": stage[dom], "dominant_kernel_share": stage[dom] / max(path_ms, 1e-9),
                          "algorithmic_bytes": b_alg,
                          "whole_path": {"ms": path_ms, "achieved": b_alg / (path_ms * 1e-3) / 1e9,
