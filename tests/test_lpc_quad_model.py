@@ -19,12 +19,13 @@ def _i32(v):
     return M.i32(v)
 
 
-def quad_predict(e, n, rss, coef, order, q, T, rng):
-    c = [[0] * T for _ in range(4)]
-    H = [[0] * T for _ in range(4)]
-    wgt = [[0] * T for _ in range(4)]
-    thr = [[0] * T for _ in range(4)]
-    for r in range(4):
+def quad_predict(e, n, rss, coef, order, q, T, rng, L=4):
+    """L lanes per stream (the kernel uses L = 4); lane r owns taps j = r*T + t."""
+    c = [[0] * T for _ in range(L)]
+    H = [[0] * T for _ in range(L)]
+    wgt = [[0] * T for _ in range(L)]
+    thr = [[0] * T for _ in range(L)]
+    for r in range(L):
         for t in range(T):
             j = r * T + t
             valid = j < order
@@ -47,21 +48,25 @@ def quad_predict(e, n, rss, coef, order, q, T, rng):
         sgbase = _i32(-base) if ee < 0 else base
         E0 = (_i32(-ee) if ee < 0 else ee) if main else 0
         rr = rneg if ee < 0 else 0
-        acc = [0] * 4
-        dp = [[0] * T for _ in range(4)]
-        st = [[0] * T for _ in range(4)]
-        mine = [0] * 4
-        for r in range(4):
+        acc = [0] * L
+        dp = [[0] * T for _ in range(L)]
+        st = [[0] * T for _ in range(L)]
+        mine = [0] * L
+        for r in range(L):
             for t in range(T - 1, -1, -1):
                 dp[r][t] = _i32(H[r][t] * nsg + sgbase)
                 acc[r] = (acc[r] + c[r][t] * dp[r][t]) & U32
                 mag = (abs(dp[r][t]) + rr) & U32
                 st[r][t] = min(((mag >> q) * wgt[r][t]) & U32, CLAMP)        # unsigned min
                 mine[r] = _i32(mine[r] + st[r][t])
-        a1 = [_i32(mine[r] + (mine[r + 1] if r < 3 else 0)) for r in range(4)]
-        for r in range(4):
-            t2 = a1[r + 2] if r < 2 else 0
-            rem = _i32(E0 - _i32(a1[r] + t2 - mine[r])) if main else -1
+        # inclusive suffix sums over the lanes (shuffle-down scan: log2(L) stages), minus the lane's own total
+        suf = list(mine)
+        d = 1
+        while d < L:
+            suf = [_i32(suf[r] + (suf[r + d] if r + d < L else 0)) for r in range(L)]
+            d *= 2
+        for r in range(L):
+            rem = _i32(E0 - _i32(suf[r] - mine[r])) if main else -1
             for t in range(T - 1, -1, -1):
                 sg = max(min(dp[r][t], 1), -1)
                 if rem > thr[r][t]:
@@ -72,8 +77,8 @@ def quad_predict(e, n, rss, coef, order, q, T, rng):
         v = _i32(_i32(v + base) + ee)
         w = _i32(prev + ee)
         oo = M.sext(v if main else w, rss)
-        below = [H[r - 1][T - 1] if r > 0 else 0 for r in range(4)]
-        for r in range(4):
+        below = [H[r - 1][T - 1] if r > 0 else 0 for r in range(L)]
+        for r in range(L):
             for t in range(T - 1, 0, -1):
                 H[r][t] = H[r][t - 1]
             H[r][0] = oo if r == 0 else below[r]
@@ -107,3 +112,20 @@ def test_quad_formulation_equals_the_reference_loop(seed):
         want = M.predict(list(e), n, rss, list(coef), order, q)
         got = quad_predict(e, n, rss, list(coef), order, q, T, rng)
         assert got == want, (order, q, rss, T)
+
+
+@pytest.mark.parametrize("lanes", [2, 8])
+def test_other_lane_counts_use_the_same_scan(lanes):
+    """not in the kernels yet: two and eight lanes per stream are the same formulation"""
+    rng = random.Random(100 + lanes)
+    for _ in range(40):
+        order = rng.randint(1, 30)
+        q = rng.randint(0, 15)
+        rss = rng.choice([16, 17, 24, 25])
+        n = rng.randint(order + 2, 120)
+        T = (order + lanes - 1) // lanes + rng.randint(0, 1)
+        lim = 1 << (rss - 2)
+        e = [rng.randint(-lim, lim) if rng.random() < 0.4 else rng.randint(-50, 50) for _ in range(n)]
+        coef = [rng.randint(-2000, 2000) for _ in range(order)]
+        want = M.predict(list(e), n, rss, list(coef), order, q)
+        assert quad_predict(e, n, rss, list(coef), order, q, T, rng, L=lanes) == want, (order, q, rss, T, lanes)
