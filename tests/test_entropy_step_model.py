@@ -46,7 +46,7 @@ class _Window:
         return ((self.value & ((1 << have) - 1)) << (32 - have)) & U32 if have else 0
 
 
-def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask):
+def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_escape=False):
     """Drop-in for alac_model.rice_decode built from the kernel's step.  `mask` is the run-length
     multiplier mask (1 << kmod) - 1 the model passes for the zero-run symbol (AlacFile.cs:236)."""
     assert mask == (1 << kmod) - 1
@@ -80,10 +80,16 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask):
         cons = s1 if e >= 2 else s0
         if esc or raw:
             cons = (32 - rsh) if raw else 9
+        # not in the kernel yet: when nine 1-bits and the raw field fit the 32-bit window
+        # together (16-bit material, and every run-length escape), the escape needs no second step
+        fused_esc = one_step_escape and esc and not raw and 9 + (32 - rsh) <= 32
+        if fused_esc:
+            dv = ((((w << 9) & U32) >> rsh) + smm1 + 1) & U32
+            cons = 9 + (32 - rsh)
         cons &= U32
         assert cons <= 32, "a step moves the cursor by at most one word"
         win.pos += cons
-        pend = esc and not raw
+        pend = esc and not raw and not fused_esc
         is_val = not pend and not run
         is_run = not pend and run
         hb = _s32(h - (_s32(h * mult) >> 9))
@@ -167,6 +173,28 @@ def test_step_state_machine_inverts_the_encoder(idx, gen, monkeypatch):
     assert M.decode_track(ck, t.mdat, t.stsz) == t.pcm, "the step state machine does not reproduce the model"
     # the encoder may store a frame uncompressed unless told not to; every compressed channel went through the step
     assert len(calls) > 0 and (CASES[idx][2].get("auto_escape", True) or len(calls) == ch * t.n_frames)
+
+
+@pytest.mark.parametrize("idx", [0, 3, 5, 10])
+def test_one_step_escape_variant(idx, gen, monkeypatch):
+    """groundwork: the escape folded into one step where the window allows it decodes the same streams"""
+    ss, ch, kw = CASES[idx]
+    kw = dict(kw)
+    rng = np.random.default_rng(5000 + idx)
+    cfg = gen.TrackCfg(ss, ch, 256, kw.pop("hist_mult", 40), kw.pop("init_hist", 10), kw.pop("kmod", 14), 44100)
+    total = 256 * 4 + 9
+    x = gen.make_signal(int(rng.integers(1, 1 << 31)), total, ss, 44100, ch).copy()
+    if kw.pop("loud", False):
+        lim = 1 << (ss - 1)
+        x[:, ::3] = rng.integers(-lim, lim, size=x[:, ::3].shape)
+    if kw.pop("quiet", False):
+        x[:] = 0
+        x[:, rng.integers(0, total, size=40)] = rng.integers(-3, 4, size=(ch, 40))
+    t = gen.build_track(cfg, x, gen.make_frames(rng, cfg, total, ch == 2, **kw))
+    ck = M.Cookie(cfg.sample_size, cfg.num_channels, cfg.max_samples_per_frame, cfg.rice_history_mult,
+                  cfg.rice_initial_history, cfg.rice_kmodifier)
+    monkeypatch.setattr(M, "rice_decode", lambda *a: step_rice_decode(*a, one_step_escape=True))
+    assert M.decode_track(ck, t.mdat, t.stsz) == t.pcm
 
 
 def test_float_exponent_is_floor_log2_on_the_whole_domain():
