@@ -414,9 +414,11 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames + 1024u;
     {
         // four-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
-        // streams from order 17 up (measured best on configs[1]: 2.72 ms; both channels 3.1 ms -- the extra
-        // warps slow the entropy lanes down).  While chunks stream in from the host the GPU has slack and
-        // the first PCM should leave as early as possible: both channels (end to end 9.9 -> 9.65 ms).
+        // streams from order 17 up (configs[1], final r1 kernels: 2.65 ms; from 25 up 2.61, from 21 up 3.24,
+        // from 13 up 3.00, none 2.86, both channels from 17 up 3.1 ms -- the extra warps slow the entropy
+        // lanes down, and which blocks end up sharing an SM matters as much as the threshold).  While chunks
+        // stream in from the host the GPU has slack and the first PCM should leave as early as possible:
+        // both channels (end to end 9.9 -> 9.65 ms).
         static const int q_last = getenv("ALACGPU_QUAD_MIN_LAST") ? atoi(getenv("ALACGPU_QUAD_MIN_LAST")) : 17;
         static const int q_first = getenv("ALACGPU_QUAD_MIN_FIRST") ? atoi(getenv("ALACGPU_QUAD_MIN_FIRST")) : -1;
         static const int q_early = getenv("ALACGPU_QUAD_MIN_EARLY") ? atoi(getenv("ALACGPU_QUAD_MIN_EARLY")) : 0;
