@@ -122,7 +122,7 @@ typedef struct alacgpu_track_cfg {
     int32_t max_samples_per_frame;  /* cookie bytes 24..27 (4096 typical)        */
     int32_t rice_history_mult;      /* cookie byte 30 (40)                       */
     int32_t rice_initial_history;   /* cookie byte 31 (10)                       */
-    int32_t rice_kmodifier;         /* cookie byte 32 (14)                       */
+    int32_t rice_kmodifier;         /* cookie byte 32 (14); 0..31 accepted        */
     int32_t sample_rate;            /* cookie bytes 44..47 (informational)       */
 } alacgpu_track_cfg;
 
