@@ -247,10 +247,8 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
     // 44 KB of unused dynamic shared memory.
     static const int pad_env = getenv("ALACGPU_SMEM_PAD") ? atoi(getenv("ALACGPU_SMEM_PAD")) : -1;
     const int pad_kb = pad_env >= 0 ? pad_env : (a.n > kSmallChunkFrames ? 44 : 0);
-    static bool attr_set = false;
-    if (pad_kb > 14 && !attr_set) {
-        cudaFuncSetAttribute(k12_entropy_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
+    if (pad_kb > 14) {      // the attribute is per device: set it on the current one, every time (a cheap driver call)
+        if (cudaError_t e = cudaFuncSetAttribute(k12_entropy_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) return e;
     }
     k12_entropy_lpc<<<grid, kK1Threads, (size_t)pad_kb * 1024, st>>>(a, lg, eblocks);
     if (tr) {

@@ -374,6 +374,22 @@ def test_tuning_environment_does_not_change_bytes(env):
     assert r.returncode == 0 and "env case ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_two_devices_with_the_big_chunk_launch_shape():
+    """the two-blocks-per-SM launch (dynamic shared memory above 48 KB) needs its function attribute on
+    EVERY device of the context"""
+    import ctypes as C
+    import os, subprocess, sys
+    from alac.net_b200 import _native as N
+    n = C.c_int32(0)
+    N.load().alacgpu_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    e = dict(os.environ, ALACGPU_SMEM_PAD="44")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_multidev_case.py"), "0", "1"], env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multidev case ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_random_payload_fuzz_matches_oracle(seed, gen, oracle):
     """valid headers + random payload bits (tests/test_fuzz_oracle_model.py): PCM and status words of
