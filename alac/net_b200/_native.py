@@ -23,6 +23,8 @@ FLAG_NO_PACK_FUSION = 0x4
 FLAG_NO_ZERO_COPY = 0x8
 FLAG_NO_QUAD_LPC = 0x10
 FLAG_FORCE_PACK_FUSION = 0x20
+FLAG_NO_FRAME_LANES = 0x40
+FLAG_FORCE_FRAME_LANES = 0x80
 
 # every symbol include/alacgpu.h declares (tests check the export table against this)
 EXPORTS = [

@@ -13,11 +13,13 @@ HOST = os.path.join(HERE, "host")
 LIB_GPU = os.path.join(HERE, "libalacgpu.so")
 LIB_HOST = os.path.join(HERE, "libalacnet_host.so")
 
-CU_SOURCES = ["k0_index.cu", "k12_decode.cu", "k3_stereo.cu", "runtime.cu"]
+CU_SOURCES = ["k0_index.cu", "k12_decode.cu", "k3_stereo.cu", "kf_frame.cu", "runtime.cu"]
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall",
 ]
+NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static"]
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -32,11 +34,24 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
     deps.append(os.path.join(ROOT, "include", "alacgpu.h"))
     if force or _newer(LIB_GPU, deps):
-        cmd = ["nvcc", *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_GPU, *srcs]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd), file=sys.stderr)
-        subprocess.check_call(cmd)
+        # one object per source, compiled side by side (the frame-lane kernels alone take ~40 s), then one link
+        from concurrent.futures import ThreadPoolExecutor
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        extra = (["-DALACGPU_CHECKED"] if os.environ.get("ALACGPU_CHECKED") == "1" else [])
+
+        def compile_one(src: str) -> str:
+            obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+            if force or _newer(obj, [src] + [d for d in deps if not d.endswith(".cu")]) or extra:
+                cmd = ["nvcc", *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                    print(" ".join(cmd), file=sys.stderr)
+                subprocess.check_call(cmd)
+            return obj
+
+        with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+            objs = list(ex.map(compile_one, srcs))
+        subprocess.check_call(["nvcc", *NVCC_LINK_FLAGS, "-o", LIB_GPU, *objs])
     return LIB_GPU
 
 

@@ -50,6 +50,12 @@ struct ChunkArgs {
     uint32_t *lpc_done;            // fused launch: predicted samples published per stream by the LPC lanes (2n entries, zeroed)
     uint32_t *pack_next;           // fused launch: next pack task (zeroed)
     uint8_t *lpc_flag;             // per stream: 1 if the stream is on the LPC work list (written by the sort)
+    // frame-lane path (kf_frame.cu): work lists of chunk-local frame slots, every class padded to whole warps
+    uint32_t *kf_list;             // [0, kf_cap) phase A, [kf_cap, 2 kf_cap) phase B, [2 kf_cap, 2 kf_cap + n) pack-only frames
+    uint32_t *kf_count;            // [0] phase A entries (padded), [1] phase B entries (padded), [2] pack-only frames;
+                                   // [8 ..] scratch of the sort (class histograms and cursors)
+    uint32_t kf_cap;               // entries per padded list: n + kKfClasses * 31 rounded up to 32
+    uint32_t *bstart;              // per frame slot: bit offset (from the frame start) where channel B's Rice stream starts
 };
 cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);   // K2 / K12 work list
@@ -61,6 +67,17 @@ cudaError_t launch_k12(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, 
 cudaError_t launch_k123(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_fix(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_k3(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);
+// frame-lane path for machine-filling chunks: class sort -> phase A (entropy + LPC of channel A in one lane per
+// frame; mono frames packed straight to PCM, stereo frames leave channel A in a half-width plane) -> phase B
+// (entropy + LPC of channel B, un-mix with the plane, PCM) -> pack-only frames (escape / failed) -> fix-up
+constexpr uint32_t kKfClasses = 256;
+inline uint32_t kf_list_cap(uint32_t n) { return (n + kKfClasses * 31u + 31u) & ~31u; }
+inline size_t kf_list_words(uint32_t n) { return 2u * (size_t)kf_list_cap(n) + n; }
+constexpr size_t kKfCountWords = 8 + 4 * 3 * kKfClasses;
+cudaError_t launch_kf_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);   // class sort -> work lists
+cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);      // phase A
+cudaError_t launch_kf_b(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);      // phase B
+cudaError_t launch_kf_rest(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);   // pack-only frames + failed-frame fix-up
 
 // position-weighted checksum of device bytes (see alacgpu_pcm_checksum)
 cudaError_t launch_checksum(const uint8_t *pcm, uint64_t global_off, uint64_t len, uint64_t *d_sum, cudaStream_t st);

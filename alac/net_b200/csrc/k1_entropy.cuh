@@ -110,6 +110,7 @@ struct BitCursor {
     uint32_t pos0;          // cursor at init, in bits from chunk 0
     uint32_t filled;        // chunks [0, filled) have been requested
 
+    template <bool kCommit = true>
     __device__ __forceinline__ void top_up()
     {
         const uint32_t want = (wpos >> 2) + kAhead;
@@ -119,7 +120,7 @@ struct BitCursor {
             cp_async16_if(ring + ((filled & (kRingChunks - 1)) << 4), base + ((uint64_t)filled << 4), go);
             filled += go;
         }
-        cp_async_commit();
+        if (kCommit) cp_async_commit();
     }
     __device__ __forceinline__ void init(const uint8_t *arena, uint64_t abs_bit, const uint8_t *ring_ptr)
     {

@@ -26,6 +26,7 @@
 #pragma once
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
+#include "lpc_tap.cuh"
 
 namespace alacgpu {
 
@@ -97,64 +98,6 @@ k0s_order_sort(const FrameDesc *__restrict__ desc, uint32_t n_frames, uint32_t *
         if (key >= 0) perm[atomicAdd(&cursor[key + (lpc_quad(d, (int)(s & 1u), key, use_quads) ? 32 : 0)], 1u)] = s;
         lpc_flag[s] = key >= 0 ? 1 : 0;
     }
-}
-
-// One tap of one sample: dot-product term + sign-LMS step, branch free.  Written in PTX so
-// the update stays two predicated instructions (nvcc otherwise turns `if (E > 0)` into a
-// branch per tap and sinks the operand computation into it).
-//   dp  = sign * (buf[b] - buf[b+order-p])              (AlacFile.cs:324, :328)
-//   acc += coef[p] * dp                                   (:303-304, sign folded out)
-//   if (E > 0) { coef[p] -= sgn(dp); E -= ((|dp| + r) >> q) * (order - p); }   (:322-330)
-__device__ __forceinline__ void lpc_tap(int32_t &c, int32_t &E, uint32_t &acc, const int32_t h, const int32_t nsg,
-                                        const int32_t sgbase, const uint32_t r, const uint32_t q, const int32_t negm)
-{
-    asm("{\n\t"
-        ".reg .s32 dp, a, u, t;\n\t"
-        ".reg .pred act;\n\t"
-        "mad.lo.s32 dp, %3, %4, %5;\n\t"
-        "setp.gt.s32 act, %1, 0;\n\t"
-        "mad.lo.s32 %2, %0, dp, %2;\n\t"
-        "abs.s32 a, dp;\n\t"
-        "max.s32 t, dp, -1;\n\t"
-        "add.s32 a, a, %6;\n\t"
-        "min.s32 t, t, 1;\n\t"
-        "shr.u32 u, a, %7;\n\t"
-        "@act sub.s32 %0, %0, t;\n\t"
-        "@act mad.lo.s32 %1, u, %8, %1;\n\t"
-        "}"
-        : "+r"(c), "+r"(E), "+r"(acc)
-        : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "r"(negm));
-}
-
-// the same with the weight -(order - p) as an immediate (one-lane warps are homogeneous in order)
-template <int NEGM>
-__device__ __forceinline__ void lpc_tap_imm(int32_t &c, int32_t &E, uint32_t &acc, const int32_t h, const int32_t nsg,
-                                            const int32_t sgbase, const uint32_t r, const uint32_t q)
-{
-    asm("{\n\t"
-        ".reg .s32 dp, a, u, t;\n\t"
-        ".reg .pred act;\n\t"
-        "mad.lo.s32 dp, %3, %4, %5;\n\t"
-        "setp.gt.s32 act, %1, 0;\n\t"
-        "mad.lo.s32 %2, %0, dp, %2;\n\t"
-        "abs.s32 a, dp;\n\t"
-        "max.s32 t, dp, -1;\n\t"
-        "add.s32 a, a, %6;\n\t"
-        "min.s32 t, t, 1;\n\t"
-        "shr.u32 u, a, %7;\n\t"
-        "@act sub.s32 %0, %0, t;\n\t"
-        "@act mad.lo.s32 %1, u, %8, %1;\n\t"
-        "}"
-        : "+r"(c), "+r"(E), "+r"(acc)
-        : "r"(h), "r"(nsg), "r"(sgbase), "r"(r), "r"(q), "n"(NEGM));
-}
-// taps pp = P .. 0 of an order-M stream (AlacFile.cs:322: newest coefficient index first)
-template <int M, int P>
-__device__ __forceinline__ void lpc_taps(int32_t (&c)[M], const int32_t (&H)[M + 1], int32_t &E, uint32_t &acc, const int32_t nsg,
-                                         const int32_t sgbase, const uint32_t r, const uint32_t q)
-{
-    lpc_tap_imm<P - M>(c[P], E, acc, H[P], nsg, sgbase, r, q);
-    if constexpr (P > 0) lpc_taps<M, P - 1>(c, H, E, acc, nsg, sgbase, r, q);
 }
 
 #ifndef ALACGPU_LPC_STREAMS_PER_WARP

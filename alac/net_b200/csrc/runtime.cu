@@ -44,6 +44,12 @@ constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
 constexpr int kSlots = 16;
 constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
+// Frame-lane path (kf_frame.cu): a device whose share of the batch holds at least this many frames has more
+// frames than lanes (148 SMs x 512 lanes), so every chunk is decoded one lane per frame and channel, with
+// chunks big enough that the class padding of the work lists stays small
+constexpr uint64_t kFrameLaneMinFrames = 65536;
+constexpr uint32_t kFrameLaneMaxChunk = 262144;
+constexpr uint64_t kFrameLanePlaneBudget = 16ull << 30;   // bytes of channel-A planes over all slots in flight
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -93,6 +99,7 @@ struct Slot {
     DevBuf<uint32_t> perm;        // K2 work list (2 entries per frame) + 1 count word at the end
     DevBuf<uint32_t> progress;    // fused launch: [0,2cf) entropy->LPC words, [2cf,4cf) LPC->pack words, 4 words of
                                   // pack task counter, then 2cf bytes of LPC work-list flags (cf = chunk frames)
+    DevBuf<uint32_t> kf;          // frame-lane path: work lists, sort counters, channel-B start bits
 };
 
 struct Device {
@@ -120,6 +127,8 @@ struct Device {
     std::vector<Chunk> chunks;
     uint32_t chunk_frames = 0;
     bool chunk_taper = false;
+    bool frame_lanes = false;         // this pipeline run decodes with the frame-lane kernels
+    int slots_n = kSlots;             // slot streams in use by this pipeline run
     std::vector<cudaEvent_t> events;
     bool resident = false;            // arena bytes + K0 results are on the device
     bool decoded = false;             // kernels ran: per-frame status is valid
@@ -431,6 +440,12 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.lpc_done = s.progress.p + cf2;
     ca.pack_next = s.progress.p + 2u * cf2;
     ca.lpc_flag = reinterpret_cast<uint8_t *>(s.progress.p + 2u * cf2 + 4u);
+    if (d.frame_lanes) {
+        ca.kf_cap = kf_list_cap(d.chunk_frames);
+        ca.kf_list = s.kf.p;
+        ca.kf_count = s.kf.p + kf_list_words(d.chunk_frames);
+        ca.bstart = ca.kf_count + kKfCountWords;
+    }
     CU(cudaEventRecord(get_event(d, ev), s.st));
     if (with_k0) {
         K0Args ka{};
@@ -449,6 +464,16 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     int fused = (ctx->opts.flags & ALACGPU_FLAG_NO_FUSION) ? 0 : (ctx->opts.flags & ALACGPU_FLAG_NO_PACK_FUSION) ? 1 : 2;
     if (fused == 2 && !pcm_override && !(ctx->opts.flags & ALACGPU_FLAG_FORCE_PACK_FUSION)) fused = 1;
     if (pcm_override) { ca.pcm = pcm_override; ca.pcm_base = 0; }      // PCM straight into host-mapped memory
+    if (d.frame_lanes) {
+        // frame-lane kernels: sort + phase A | phase B | pack-only frames + fix-up (timing slots: entropy, lpc, stereo)
+        if (with_decode) { CU(launch_kf_sort(ca, s.st, launches)); CU(launch_kf_a(ca, s.st, launches)); }
+        CU(cudaEventRecord(get_event(d, ev + 2), s.st));
+        if (with_decode) CU(launch_kf_b(ca, s.st, launches));
+        CU(cudaEventRecord(get_event(d, ev + 3), s.st));
+        if (with_decode) CU(launch_kf_rest(ca, s.st, launches));
+        CU(cudaEventRecord(get_event(d, ev + 4), s.st));
+        return ALACGPU_OK;
+    }
     if (with_decode) {
         CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
         if (fused) CU(cudaMemsetAsync(s.progress.p, 0, (2u * cf2 + 4u) * sizeof(uint32_t), s.st));
@@ -532,18 +557,26 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
     // copy and no D2H stage.
     // chunk size: as much as possible in flight at once when the bytes are already resident;
     // ~kSlots chunks when streaming from the host so copies and kernels overlap
+    static const uint64_t kf_min = getenv("ALACGPU_KF_MIN") ? strtoull(getenv("ALACGPU_KF_MIN"), nullptr, 10) : kFrameLaneMinFrames;
+    auto frame_lanes_for = [&](const Device &d) {
+        if (ctx->opts.flags & (ALACGPU_FLAG_NO_FRAME_LANES | ALACGPU_FLAG_NO_FUSION)) return false;
+        if (ctx->opts.flags & ALACGPU_FLAG_FORCE_FRAME_LANES) return true;
+        return d.f_hi - d.f_lo >= kf_min;
+    };
     auto chunk_frames_for = [&](const Device &d) {
         const uint64_t n_local = d.f_hi - d.f_lo;
+        const bool kf = frame_lanes_for(d);
+        const uint32_t cap = kf ? kFrameLaneMaxChunk : kMaxChunkFrames;
         uint32_t cf = ctx->opts.chunk_frames;
         if (!cf) {
-            if (stage) cf = (uint32_t)std::max<uint64_t>(256, (n_local + kSlots - 1) / kSlots);
-            else cf = (uint32_t)std::min<uint64_t>(n_local, kMaxChunkFrames);
+            if (stage) cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
+            else cf = (uint32_t)std::min<uint64_t>(n_local, cap);
         }
-        return std::min<uint32_t>((cf + 31u) & ~31u, kMaxChunkFrames);
+        return std::min<uint32_t>((cf + 31u) & ~31u, cap);
     };
     bool all_fully_fused = !stage;
     for (const Device &d : ctx->devs)
-        if (d.f_hi > d.f_lo && chunk_frames_for(d) > kFullFusionMaxFrames) all_fully_fused = false;
+        if (d.f_hi > d.f_lo && (chunk_frames_for(d) > kFullFusionMaxFrames || frame_lanes_for(d))) all_fully_fused = false;
     uint8_t *zc = nullptr;
     if (pcm_dst && decode && all_fully_fused && !(ctx->opts.flags & (ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_PACK_FUSION | ALACGPU_FLAG_NO_ZERO_COPY))) {
         cudaPointerAttributes at{};
@@ -565,15 +598,25 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (!n_local) continue;
         CU(cudaSetDevice(d.id));
         const uint32_t cf = chunk_frames_for(d);
+        d.frame_lanes = frame_lanes_for(d);
         static const bool no_taper = getenv("ALACGPU_NO_TAPER") != nullptr;
-        build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper);
+        build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper && !d.frame_lanes);
         const size_t n_chunks = d.chunks.size();
-        const int slots_used = (int)std::min<size_t>(kSlots, n_chunks);
+        // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
+        d.slots_n = kSlots;
+        if (d.frame_lanes)
+            d.slots_n = (int)std::max<uint64_t>(3, std::min<uint64_t>(kSlots, kFrameLanePlaneBudget / ((uint64_t)cf * d.ns * 4u)));
+        const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
         if (decode)
             for (int s = 0; s < slots_used; s++) {
-                CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
-                CU(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
-                CU(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
+                if (d.frame_lanes) {
+                    CU(d.slots[s].planes.reserve((size_t)cf * d.ns + 64u));          // one row per frame (channel A)
+                    CU(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
+                } else {
+                    CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
+                    CU(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
+                    CU(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
+                }
             }
         get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
         CU(cudaEventRecord(d.events[0], d.slots[0].st));
@@ -584,7 +627,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         }
         for (size_t ci = 0; ci < n_chunks; ci++) {
             const Chunk &c = d.chunks[ci];
-            Slot &s = d.slots[ci % kSlots];
+            Slot &s = d.slots[ci % (size_t)d.slots_n];
             const size_t ev = kEvBase + ci * kEvPerChunk;
             if (stage) {
                 for (uint32_t k = c.copy_lo; k < c.copy_hi; k++)
@@ -603,8 +646,8 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
             chunks_total++;
         }
         // join: slot 0 waits for the last chunk of every other slot, then stamps the end
-        for (size_t ci = n_chunks > (size_t)kSlots ? n_chunks - kSlots : 0; ci < n_chunks; ci++)
-            if (ci % kSlots != 0) CU(cudaStreamWaitEvent(d.slots[0].st, d.events[kEvBase + ci * kEvPerChunk + 4], 0));
+        for (size_t ci = n_chunks > (size_t)d.slots_n ? n_chunks - (size_t)d.slots_n : 0; ci < n_chunks; ci++)
+            if (ci % (size_t)d.slots_n != 0) CU(cudaStreamWaitEvent(d.slots[0].st, d.events[kEvBase + ci * kEvPerChunk + 4], 0));
         CU(cudaEventRecord(d.events[1], d.slots[0].st));
         if (pcm_dst && !zc) CU(cudaEventRecord(d.events[3], d.st_d2h));
     }
@@ -746,7 +789,7 @@ int32_t alacgpu_destroy(alacgpu_ctx *ctx)
         cudaDeviceSynchronize();
         d.arena.release(); d.refs.release(); d.cfgs.release(); d.desc.release(); d.coefs.release();
         d.expect_len.release(); d.frame_off.release(); d.scalars.release(); d.pcm.release();
-        for (Slot &s : d.slots) { s.planes.release(); s.perm.release(); s.progress.release(); if (s.st) cudaStreamDestroy(s.st); }
+        for (Slot &s : d.slots) { s.planes.release(); s.perm.release(); s.progress.release(); s.kf.release(); if (s.st) cudaStreamDestroy(s.st); }
         for (cudaEvent_t e : d.events) cudaEventDestroy(e);
         if (d.st_h2d) cudaStreamDestroy(d.st_h2d);
         if (d.st_d2h) cudaStreamDestroy(d.st_d2h);

@@ -1,20 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- decoded PCM Msamples/s of the ALAC frame-decode path on B200.
 
-    python bench.py --gpus N --steps K --warmup W            (ours, N=1)
-    torchrun ... bench.py --gpus N --steps K --warmup W      (ours, N>1: one rank per GPU)
-    python bench.py --impl reference ...                     (CPU oracle on all host cores)
+    python bench.py --gpus 1 --steps K --warmup W             (ours, N=1)
+    torchrun ... bench.py --gpus N --steps K --warmup W       (ours, N>1: one rank per GPU)
+    python bench.py --impl reference ...                      (the oracle's C port on all host cores)
+    python bench.py --gpus N --single-process                 (ONE alacgpu context over N GPUs, one process)
 
-A "step" is one pass of the whole kernel path (K0 header index + order sort ->
-K12 fused entropy + LPC -> K3 stereo/pack) over the workload with the compressed
-input already resident in HBM.  `value` = channel values decoded by all ranks / max-over-ranks time.
-`e2e` is the same metric through the C ABI with HOST buffers: every step stages
-the mdat from pinned host memory (H2D), decodes and copies the PCM back (D2H).
+Workloads (BASELINE.json):
+  N = 1  configs[3]: 1,000 synthetic 16-bit stereo 44.1 kHz tracks x 252 s (~70 h) decoded in ONE
+         alacgpu_decode_all on one B200.  `--unique` distinct tracks are generated and replicated PHYSICALLY
+         (every replica is staged separately in HBM: 29.5 GB compressed in, 44.5 GB PCM out per step).
+         Secondary `latency_legs`: configs[0], [1], [2] (single tracks, fewer frames than the GPU has lanes).
+  N > 1  configs[4]: the 16/24-bit mono/stereo mix (track i is of kind i mod 10), 1,250 tracks per GPU
+         (10,000 at N = 8), cut FRAME-WISE into N contiguous ranges balanced by compressed bytes
+         (alac.net_b200.shard.rank_slices == alacgpu_plan_partition); every rank stages and decodes only its
+         range.  No data-path collective: NCCL carries the barrier and the max/sum of the timings only.
 
-Workload (default): BASELINE.json configs[1] -- synthetic 24-bit stereo 96 kHz
-ALAC, 10 min, 4096-sample frames, LPC order 1..31, wasted bytes 0/1/2.  Under
-N ranks every rank decodes its own track of that shape (seed + rank): frames
-are independent, no collective (scaling: weak).
+A "step" is one pass of the whole kernel path (header pre-pass + decode kernels) over the workload with the
+compressed input already resident in HBM; `value` = channel values decoded by all ranks / max-over-ranks time.
+`e2e` is the same metric through the C ABI with HOST buffers: every step clears the context, adds every
+track again (H2D of all mdat bytes), decodes and copies all PCM back (D2H), in as few decode_all calls as the
+host output buffer allows.  Parity (device checksum of the decoded PCM == checksum of the encoder's input,
+frame status all OK, byte compare of the host copy) is checked in the run before anything is timed.
 """
 from __future__ import annotations
 
@@ -32,34 +39,118 @@ sys.path.insert(0, ROOT)
 
 METRIC = "decoded PCM Msamples/s"
 UNIT = "Msamples/s"
+M64 = (1 << 64) - 1
 
 
 # ---------------------------------------------------------------------------
-# workload
+# workloads
 # ---------------------------------------------------------------------------
-def make_workload(name: str, rank: int, scale: float):
+class Corpus:
+    """`uniq`: distinct tracks; `index[j]`: which of them global track j is a (physical) replica of."""
+
+    def __init__(self, uniq, index, desc, key):
+        self.uniq, self.index, self.desc, self.key = uniq, np.asarray(index, dtype=np.int64), desc, key
+        self._sums = None
+
+    @property
+    def n_tracks(self):
+        return int(self.index.size)
+
+    def track(self, j):
+        return self.uniq[int(self.index[j])]
+
+    def totals(self):
+        cnt = np.bincount(self.index, minlength=len(self.uniq))
+        f = lambda g: int(sum(int(c) * g(t) for c, t in zip(cnt, self.uniq)))
+        return {"frames": f(lambda t: t.n_frames), "samples": f(lambda t: t.n_samples),
+                "pcm_bytes": f(lambda t: len(t.pcm)), "compressed_bytes": f(lambda t: len(t.mdat))}
+
+    def sums(self):
+        """(S0, S1) of every distinct track's PCM: sum of 8-byte words, and sum of word * (2 j + 1)."""
+        if self._sums is None:
+            from alac.net_b200 import host_checksum
+            out = []
+            for t in self.uniq:
+                a = np.frombuffer(t.pcm, dtype=np.uint8)
+                pad = (-a.size) % 8
+                if pad:
+                    a = np.concatenate([a, np.zeros(pad, dtype=np.uint8)])
+                with np.errstate(over="ignore"):
+                    s0 = int(np.sum(a.view("<u8"), dtype=np.uint64))
+                out.append((s0, host_checksum(t.pcm)))
+            self._sums = out
+        return self._sums
+
+
+def make_corpus(name: str, world: int, args) -> Corpus:
     from tools.alacgen import alacgen as g
     g.build_encoder()
+    s = args.scale
+    if name == "config1":
+        return Corpus([g.track_16_stereo(g.SEED_BASE + 1, 60.0 * s)], [0],
+                      "configs[0]: synthetic 16-bit stereo 44.1 kHz ALAC, 60 s, 4096-sample frames", name)
     if name == "config2":
-        tracks = [g.track_24_stereo(g.SEED_BASE + 2 + 7919 * rank, 600.0 * scale)]
-        desc = "configs[1]: synthetic 24-bit stereo 96 kHz ALAC, 10 min, 4096-sample frames, LPC order 1..31, wasted bytes 0/1/2"
-    elif name == "config1":
-        tracks = [g.track_16_stereo(g.SEED_BASE + 1 + 7919 * rank, 60.0 * scale)]
-        desc = "configs[0]: synthetic 16-bit stereo 44.1 kHz ALAC, 60 s, 4096-sample frames"
-    elif name == "config3":
-        tracks = [g.track_16_mono_mixed(g.SEED_BASE + 3 + 7919 * rank, 60.0 * scale)]
-        desc = "configs[2]: 16-bit mono mixing compressed / uncompressed / Rice-escape frames"
-    elif name.startswith("config4"):
-        # configs[3]: 1,000 16-bit stereo tracks (~70 h).  `unique` distinct tracks are generated
-        # and replicated PHYSICALLY (each replica is staged separately in HBM).
-        unique = 8
-        base = [g.track_16_stereo(g.SEED_BASE + 1000 + i + 7919 * rank, 252.0 * scale) for i in range(unique)]
-        n = int(name.split(":")[1]) if ":" in name else 1000
-        tracks = [base[i % unique] for i in range(n)]
-        desc = f"configs[3]: batch of {n} synthetic 16-bit stereo tracks x 252 s ({unique} unique, replicated physically)"
-    else:
-        raise SystemExit(f"unknown workload {name}")
-    return tracks, desc
+        return Corpus([g.track_24_stereo(g.SEED_BASE + 2, 600.0 * s)], [0],
+                      "configs[1]: synthetic 24-bit stereo 96 kHz ALAC, 10 min, 4096-sample frames, LPC order 1..31, "
+                      "wasted bytes 0/1/2", name)
+    if name == "config3":
+        return Corpus([g.track_16_mono_mixed(g.SEED_BASE + 3, 60.0 * s)], [0],
+                      "configs[2]: 16-bit mono mixing compressed / uncompressed / Rice-escape frames", name)
+    if name == "config4":
+        n = args.tracks or 1000
+        u = max(1, min(args.unique, n))
+        uniq = [g.track_16_stereo(g.SEED_BASE + 1000 + i, 252.0 * s) for i in range(u)]
+        return Corpus(uniq, np.arange(n) % u,
+                      f"configs[3]: batch of {n} synthetic 16-bit stereo 44.1 kHz tracks x {252.0 * s:g} s decoded in one "
+                      f"call ({u} distinct tracks, every replica staged separately in HBM)", name)
+    if name == "config5":
+        per = args.tracks_per_gpu or 1250
+        n = args.tracks or per * world
+        u = 10 * max(1, args.unique_per_kind)
+        uniq = [g.corpus_track(i, 252.0 * s) for i in range(u)]
+        return Corpus(uniq, np.arange(n) % u,
+                      f"configs[4]: {n}-track mixed corpus x {252.0 * s:g} s (track i is of kind i mod 10: 0-4 16-bit stereo "
+                      f"44.1 kHz, 5-6 16-bit mono, 7-8 24-bit stereo 48 kHz, 9 24-bit mono 96 kHz; {u} distinct tracks, "
+                      f"replicas staged separately), {per} tracks per GPU, cut frame-wise over {world} GPU(s)", name)
+    raise SystemExit(f"unknown workload {name}")
+
+
+class Piece:
+    """Frames [f_lo, f_hi) of global track j (a whole track unless a shard boundary cuts it)."""
+    __slots__ = ("j", "u", "f_lo", "f_hi", "b_lo", "b_hi", "p_lo", "p_hi")
+
+    def __init__(self, corpus, j, f_lo=None, f_hi=None, b_lo=None, b_hi=None):
+        t = corpus.track(j)
+        self.j, self.u = j, int(corpus.index[j])
+        self.f_lo, self.f_hi = (0, t.n_frames) if f_lo is None else (f_lo, f_hi)
+        if b_lo is None:
+            offs = np.concatenate([[0], np.cumsum(t.stsz.astype(np.int64))])
+            b_lo, b_hi = int(offs[self.f_lo]), int(offs[self.f_hi])
+        self.b_lo, self.b_hi = b_lo, b_hi
+        bpf = (t.cfg.sample_size // 8) * t.cfg.num_channels
+        ps = np.concatenate([[0], np.cumsum(t.frame_samples.astype(np.int64))]) * bpf
+        self.p_lo, self.p_hi = int(ps[self.f_lo]), int(ps[self.f_hi])
+
+    def whole(self, corpus):
+        return self.f_lo == 0 and self.f_hi == corpus.track(self.j).n_frames
+
+
+def rank_pieces(corpus: Corpus, world: int, rank: int):
+    if world == 1:
+        out = []
+        cache = {}
+        for j in range(corpus.n_tracks):
+            u = int(corpus.index[j])
+            if u not in cache:
+                cache[u] = Piece(corpus, j)
+            c = cache[u]
+            p = Piece.__new__(Piece)
+            p.j, p.u, p.f_lo, p.f_hi, p.b_lo, p.b_hi, p.p_lo, p.p_hi = j, u, c.f_lo, c.f_hi, c.b_lo, c.b_hi, c.p_lo, c.p_hi
+            out.append(p)
+        return out
+    from alac.net_b200.shard import rank_slices
+    sl = rank_slices([corpus.track(j).stsz for j in range(corpus.n_tracks)], world, rank)
+    return [Piece(corpus, s.track, s.frame_lo, s.frame_hi, s.byte_lo, s.byte_hi) for s in sl]
 
 
 class ClockSampler(threading.Thread):
@@ -124,28 +215,43 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def mem_available() -> int:
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 64 << 30
+
+
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores
+# CPU arm: the oracle's C port on the host cores
 # ---------------------------------------------------------------------------
-def cpu_decode_rate(tracks, budget_frames_per_thread: int, threads: int, repeats: int = 1):
-    """One slice of frames per thread (frames are independent, so a thread decodes its own
-    contiguous range exactly as one AlacContext would pump it).  -> (Msamples/s, sample text)."""
+def cpu_decode_rate(corpus: Corpus, frames_per_thread: int, threads: int, repeats: int = 1):
+    """One contiguous frame range per thread (frames are independent, so a thread decodes its range exactly
+    as one AlacContext would pump it); thread i takes its range from distinct track i mod U, so a mixed corpus
+    is sampled in its mix.  -> (Msamples/s, sample text, seconds)."""
     from oracle import oracle as o
     o.build()
-    t = tracks[0]
-    cfg = o.cfg_from(t.cfg)
-    nf = t.n_frames
-    per = max(1, min(budget_frames_per_thread, nf // max(1, threads)))
-    offs = np.concatenate([[0], np.cumsum(t.stsz.astype(np.int64))])
-    mdat = np.frombuffer(t.mdat, dtype=np.uint8)
     jobs = []
+    samples = 0
     for i in range(threads):
-        a = (i * per) % max(1, nf - per + 1)
-        jobs.append((a, a + per))
-    samples = sum(int(t.frame_samples[a:b].sum()) for a, b in jobs) * t.cfg.num_channels
+        t = corpus.uniq[i % len(corpus.uniq)]
+        per = max(1, min(frames_per_thread, t.n_frames))
+        a = (i * per) % max(1, t.n_frames - per + 1)
+        offs = np.concatenate([[0], np.cumsum(t.stsz.astype(np.int64))])
+        mdat = np.frombuffer(t.mdat, dtype=np.uint8)
+        jobs.append((o.cfg_from(t.cfg), mdat[offs[a]:offs[a + per]].tobytes(), t.stsz[a:a + per]))
+        samples += int(t.frame_samples[a:a + per].sum()) * t.cfg.num_channels
 
-    def work(a, b):
-        o.decode_track(cfg, mdat[offs[a]:offs[b]].tobytes(), t.stsz[a:b])
+    def work(cfg, data, stsz):
+        o.decode_track(cfg, data, stsz)
 
     best = None
     for _ in range(repeats):
@@ -157,24 +263,34 @@ def cpu_decode_rate(tracks, budget_frames_per_thread: int, threads: int, repeats
             th.join()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return samples / best / 1e6, f"{threads} threads x {per} frames ({samples} samples) of the workload, best of {repeats}", best
+    text = (f"{threads} threads x {frames_per_thread} frames ({samples} samples) of the workload"
+            + (f", thread i on distinct track i mod {len(corpus.uniq)}" if len(corpus.uniq) > 1 else "") + f", best of {repeats}")
+    return samples / best / 1e6, text, best
+
+
+def default_workload(args, world):
+    if args.workload != "auto":
+        return args.workload
+    return "config4" if world == 1 else "config5"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    tracks, desc = make_workload(args.workload, 0, args.scale)
-    cores = os.cpu_count() or 1
-    # bounded sample: calibrate on a small slice, then size each step so the whole
-    # --steps/--warmup run stays near a 90 s budget (at most the full workload per step)
-    _, _, dt0 = cpu_decode_rate(tracks, 8, cores)
+    world = max(1, args.gpus)
+    corpus = make_corpus(default_workload(args, world), world, args)
+    cores = host_cores()
+    # bounded sample: calibrate on a small slice, then size each step so the whole --steps/--warmup run stays
+    # near a 90 s budget (at most 2048 frames per thread and step)
+    _, _, dt0 = cpu_decode_rate(corpus, 8, cores)
     per_frame = dt0 / 8.0
     budget = 90.0 / max(1, args.steps + args.warmup)
-    per = int(max(8, min(tracks[0].n_frames // cores, budget / max(per_frame, 1e-6))))
+    per = int(max(8, min(2048, budget / max(per_frame, 1e-6))))
     vals = []
+    sample = ""
     for i in range(args.warmup + args.steps):
-        v, sample, dt = cpu_decode_rate(tracks, per, cores)
+        v, sample, dt = cpu_decode_rate(corpus, per, cores)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
@@ -183,7 +299,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": desc, "scale": args.scale},
+        "config": {"workload": corpus.desc, "scale": args.scale},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + " per step; oracle/ C restatement of AlacFile.cs (the C# reference cannot run: no .NET in the image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,61 +311,172 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-def batch_leg(args, local):
-    """Throughput regime (not the headline): a configs[3]-shaped batch -- many 16-bit stereo tracks in ONE
-    decode_all -- where there are more frames than lanes and the kernels are issue-bound, not latency-bound."""
-    from alac.net_b200 import BatchDecoder, PinnedBuffer
-    tracks, desc = make_workload(f"config4:{args.batch_tracks}", 0, 1.0)
-    pinned = {}
-    for t in tracks:                     # replicas share the pinned source; each is staged separately in HBM
-        if id(t) not in pinned:
-            pb = PinnedBuffer(len(t.mdat))
-            pb.array[:] = np.frombuffer(t.mdat, dtype=np.uint8)
-            pinned[id(t)] = pb
-    samples = sum(t.n_samples for t in tracks)
-    with BatchDecoder(devices=[local], flags=args.flags | (2 if args.no_fusion else 0)) as dec:
-        for t in tracks:
-            dec.add_track(t.cfg, pinned[id(t)], t.stsz)
-        dec.prepare()
-        dec.decode_all(False, want_status=False)
-        ok = dec.checksum() == sum(host_checksum_at(dec, i, t) for i, t in enumerate(tracks)) % (1 << 64)
-        if not ok:
-            raise SystemExit("bench.py: batch leg PCM checksum differs from the encoder's input")
-        ms = []
-        for _ in range(3):
-            dec.reindex()
-            dec.decode_all(False, want_status=False)
-            tm = dec.timing()
-            ms.append(tm["kernels_ms"])      # one pipeline: K0 + sort + K12 + K3 (reindex is lazy)
-        t_ms = float(np.median(ms))
-        stage = {k: tm[k] for k in ("index_ms", "entropy_ms", "lpc_ms", "stereo_ms", "kernels_ms", "chunks")}
-    comp = sum(len(t.mdat) for t in tracks)
-    pcm = sum(len(t.pcm) for t in tracks)
-    return {"workload": desc, "frames": sum(t.n_frames for t in tracks), "samples": samples,
-            "device_ms": t_ms, "stage_ms": stage, "value": samples / (t_ms * 1e-3) / 1e6, "unit": UNIT,
-            "algorithmic_bytes": comp + pcm, "hbm_gbs": (comp + pcm) / (t_ms * 1e-3) / 1e9,
-            "parity": "device checksum of the resident PCM == checksum of the encoder's input"}
+class Staged:
+    """Pinned host copies of the distinct tracks' mdat bytes + helpers to add pieces to a decoder."""
+
+    def __init__(self, corpus: Corpus, pinned: bool = True):
+        from alac.net_b200 import PinnedBuffer
+        self.corpus = corpus
+        self.src, self._keep = [], []
+        for t in corpus.uniq:
+            if pinned:
+                pb = PinnedBuffer(len(t.mdat))
+                pb.array[:] = np.frombuffer(t.mdat, dtype=np.uint8)
+                self.src.append(pb.array)
+                self._keep.append(pb)
+            else:
+                self.src.append(np.frombuffer(t.mdat, dtype=np.uint8).copy())       # plain pageable memory
+
+    def add(self, dec, p: Piece):
+        t = self.corpus.uniq[p.u]
+        dec.add_track(t.cfg, self.src[p.u][p.b_lo:p.b_hi], t.stsz[p.f_lo:p.f_hi])
 
 
-def host_checksum_at(dec, i, t):
+def expected_checksum(corpus: Corpus, dec, pieces) -> int:
+    """Checksum of the encoder's input laid out like the decoder's output, from per-track sums:
+    sum_j w_j (2 (first + j) + 1) = S1 + 2 first S0 for a whole track placed at 8-byte word `first`."""
     from alac.net_b200 import host_checksum
-    off, ln = dec.track_pcm_bytes(i)
-    return host_checksum(t.pcm, first_word=off // 8)
+    sums = corpus.sums()
+    total = 0
+    for i, p in enumerate(pieces):
+        off, ln = dec.track_pcm_bytes(i)
+        assert ln == p.p_hi - p.p_lo, (i, ln, p.p_hi - p.p_lo)
+        if p.whole(corpus):
+            s0, s1 = sums[p.u]
+            total += s1 + 2 * (off // 8) * s0
+        else:
+            total += host_checksum(corpus.uniq[p.u].pcm[p.p_lo:p.p_hi], first_word=off // 8)
+    return total & M64
+
+
+def check_host_copy(corpus, pieces, out, off, ln, every: int = 1) -> bool:
+    ok = True
+    for i in range(0, len(pieces), every):
+        p = pieces[i]
+        ref = np.frombuffer(corpus.uniq[p.u].pcm, dtype=np.uint8)[p.p_lo:p.p_hi]
+        ok = ok and int(ln[i]) == ref.size and np.array_equal(out[int(off[i]):int(off[i] + ln[i])], ref)
+    return ok
+
+
+def groups_for(pieces, cap_bytes):
+    """consecutive pieces whose PCM (with 256-byte alignment per piece) fits cap_bytes"""
+    out, cur, used = [], [], 0
+    for p in pieces:
+        need = (p.p_hi - p.p_lo + 255) // 256 * 256
+        if cur and used + need > cap_bytes:
+            out.append(cur)
+            cur, used = [], 0
+        cur.append(p)
+        used += need
+    if cur:
+        out.append(cur)
+    return out
+
+
+def e2e_leg(dec, staged, pieces, steps, warm, barrier, pinned_out: bool, cap_bytes: int):
+    """clear -> add every piece (H2D of all mdat bytes) -> decode_all into a HOST buffer (D2H of all PCM), per
+    group of pieces that fits the output buffer.  -> (ms per step, groups, last timing, parity ok)."""
+    from alac.net_b200 import PinnedBuffer
+    groups = groups_for(pieces, cap_bytes)
+    need = max(sum((p.p_hi - p.p_lo + 255) // 256 * 256 for p in g) for g in groups)
+    if pinned_out:
+        buf = PinnedBuffer(need)
+        arr = buf.array
+    else:
+        buf = None
+        arr = np.empty(need, dtype=np.uint8)
+    ok = True
+
+    def step(check=False):
+        nonlocal ok
+        for g in groups:
+            dec.clear()
+            for p in g:
+                staged.add(dec, p)
+            out, off, ln, _ = dec.decode_all(arr, want_status=False)
+            if check:
+                ok = ok and check_host_copy(staged.corpus, g, out, off, ln, every=max(1, len(g) // 24))
+
+    step(check=True)
+    for _ in range(max(0, warm - 1)):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    tm = dec.timing()
+    if buf is not None:
+        buf.free()
+    return ms, len(groups), tm, ok
+
+
+def latency_leg(name, args, local):
+    """A single-track config (fewer frames than lanes): device-resident and end-to-end time of one decode."""
+    from alac.net_b200 import BatchDecoder, PinnedBuffer, host_checksum
+    corpus = make_corpus(name, 1, args)
+    t = corpus.uniq[0]
+    staged = Staged(corpus)
+    with BatchDecoder(devices=[local], flags=args.flags) as dec:
+        staged.add(dec, Piece(corpus, 0))
+        total = dec.prepare()
+        host = PinnedBuffer(total)
+        out, off, ln, status = dec.decode_all(host)
+        ok = bool((status == 0).all()) and out[:int(ln[0])].tobytes() == t.pcm
+        dec.decode_all(False, want_status=False)
+        ok = ok and dec.checksum() == host_checksum(t.pcm)
+        if not ok:
+            raise SystemExit(f"bench.py: latency leg {name}: decoded PCM differs from the encoder's input")
+        ms = []
+        for i in range(3 + args.latency_steps):
+            dec.reindex()
+            t0 = time.perf_counter()
+            dec.decode_all(False, want_status=False)
+            dt = (time.perf_counter() - t0) * 1e3
+            if i >= 3:
+                ms.append((dt, dec.timing()["kernels_ms"]))
+        wall = float(np.median([a for a, _ in ms]))
+        dev = float(np.median([b for _, b in ms]))
+        e = []
+        for i in range(2 + max(3, args.latency_steps // 4)):
+            t0 = time.perf_counter()
+            dec.clear()
+            staged.add(dec, Piece(corpus, 0))
+            dec.decode_all(host, want_status=False)
+            if i >= 2:
+                e.append((time.perf_counter() - t0) * 1e3)
+        host.free()
+    e2e = float(np.median(e))
+    return {"workload": corpus.desc, "frames": t.n_frames, "samples": t.n_samples,
+            "device_ms": dev, "wall_ms": wall, "value": t.n_samples / (wall * 1e-3) / 1e6,
+            "e2e_ms": e2e, "e2e_value": t.n_samples / (e2e * 1e-3) / 1e6, "unit": UNIT,
+            "parity": "bit-exact vs the encoder's input + device checksum"}
+
+
+def load_profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from alac.net_b200 import BatchDecoder, PinnedBuffer, host_checksum
+    from alac.net_b200 import BatchDecoder
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the decode path has no CPU fallback)")
-    torch.cuda.set_device(local)
+    single = args.single_process and world == 1 and args.gpus > 1
+    devices = list(range(args.gpus)) if single else [local]
+    torch.cuda.set_device(devices[0])
     from alac.net_b200.shard import bind_to_gpu_numa_node
-    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"numa_node": None, "cpus": None}
+    numa = bind_to_gpu_numa_node(local) if not (args.no_numa_bind or single) else {"numa_node": None, "cpus": None}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout at communicator creation; stdout carries exactly one
@@ -272,156 +499,188 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    tracks, desc = make_workload(args.workload, rank, args.scale)
-    samples = sum(t.n_samples for t in tracks)
-    pcm_bytes = sum(len(t.pcm) for t in tracks)
-    comp_bytes = sum(len(t.mdat) for t in tracks)
-    n_frames = sum(t.n_frames for t in tracks)
+    shards = world if world > 1 else (args.gpus if single else 1)
+    name = default_workload(args, shards)
+    corpus = make_corpus(name, shards, args)
+    pieces = rank_pieces(corpus, world, rank)
+    staged = Staged(corpus)
+    n_frames = sum(p.f_hi - p.f_lo for p in pieces)
+    samples = sum((p.p_hi - p.p_lo) // (corpus.uniq[p.u].cfg.sample_size // 8) for p in pieces)
+    pcm_bytes = sum(p.p_hi - p.p_lo for p in pieces)
+    comp_bytes = sum(p.b_hi - p.b_lo for p in pieces)
 
-    # pinned host copies of the inputs (e2e stages from these every step)
-    pinned = []
-    for t in tracks:
-        pb = PinnedBuffer(len(t.mdat))
-        pb.array[:] = np.frombuffer(t.mdat, dtype=np.uint8)
-        pinned.append(pb)
-
-    dec = BatchDecoder(devices=[local], chunk_frames=args.chunk_frames, entropy_lanes=args.entropy_lanes,
-                       flags=args.flags | (2 if args.no_fusion else 0))
-    for t, pb in zip(tracks, pinned):
-        dec.add_track(t.cfg, pb, t.stsz)
+    dec = BatchDecoder(devices=devices, chunk_frames=args.chunk_frames, entropy_lanes=args.entropy_lanes, flags=args.flags)
+    t_setup = time.perf_counter()
+    for p in pieces:
+        staged.add(dec, p)
     total = dec.prepare()              # stage the mdat in HBM + header pre-pass: inputs resident
-    host_out = PinnedBuffer(total)
+    t_setup = time.perf_counter() - t_setup
 
-    # ---- parity in the same run: full PCM vs the encoder's input + checksum ----
-    out, off, ln, status = dec.decode_all(host_out)
+    # ---- parity in the same run, before anything is timed ------------------------------------------
+    _, _, _, status = dec.decode_all(False, want_status=True)
     ok = bool((status == 0).all())
-    for t, o_, l_ in zip(tracks, off, ln):
-        ok = ok and out[int(o_):int(o_ + l_)].tobytes() == t.pcm
-    dec.decode_all(False, want_status=False)      # device-resident copy for the on-device checksum
     dev_sum = dec.checksum()
-    ok = ok and dev_sum == host_checksum(out[:total])
+    exp_sum = expected_checksum(corpus, dec, pieces)
+    ok = ok and dev_sum == exp_sum
     if not ok:
-        raise SystemExit("bench.py: decoded PCM does not match the encoder's input -- refusing to time a wrong decoder")
+        raise SystemExit(f"bench.py: rank {rank}: decoded PCM does not match the encoder's input "
+                         f"(status ok {bool((status == 0).all())}, checksum {dev_sum:#x} vs {exp_sum:#x}) -- refusing to time a wrong decoder")
 
-    # ---- device-resident steps ----------------------------------------------------
+    # ---- device-resident steps ----------------------------------------------------------------------
     def step():
         dec.reindex()                 # marks the frame index stale: K0 runs again inside the next decode_all
         dec.decode_all(False, want_status=False)
         return dec.timing()
 
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(devices[0])
     barrier()
     sampler.start()
     t0 = time.perf_counter()
     acc = {"index_ms": 0.0, "entropy_ms": 0.0, "lpc_ms": 0.0, "stereo_ms": 0.0, "kernels_ms": 0.0}
     launches = 0
+    chunks = 0
     for _ in range(args.steps):
         tm = step()
         for k in acc:
             acc[k] += tm[k]
         launches += tm["kernel_launches"]
+        chunks = tm["chunks"]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.finish()
-    dev_ms = acc["kernels_ms"] / args.steps     # CUDA events on the launch stream: K0 + sort + K12 + K3 in one pipeline
+    dev_ms = acc["kernels_ms"] / args.steps     # CUDA events on the launch streams: first launch -> last kernel done
     wall_ms = wall * 1e3 / args.steps
+    # a timed step must not have produced a wrong frame silently: the checksum of the LAST timed step's PCM
+    if dec.checksum() != exp_sum:
+        raise SystemExit(f"bench.py: rank {rank}: PCM of the last timed step differs from the encoder's input")
 
-    # ---- end to end through the C ABI with host buffers -----------------------------
-    def e2e_step():
-        dec.clear()
-        for t, pb in zip(tracks, pinned):
-            dec.add_track(t.cfg, pb, t.stsz)
-        dec.decode_all(host_out, want_status=False)
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------
+    e2e = None
+    if args.e2e_steps > 0:
+        avail = mem_available()
+        cap = min(total + 4096, max(1 << 30, int(avail * 0.45) // (world if world > 1 else 1)))
+        if args.e2e_buffer_gb > 0:
+            cap = min(cap, int(args.e2e_buffer_gb * (1 << 30)))
+        ms, ngroups, tm_e2e, ok_e = e2e_leg(dec, staged, pieces, args.e2e_steps, 2, barrier, True, cap)
+        if not ok_e:
+            raise SystemExit(f"bench.py: rank {rank}: end-to-end PCM differs from the encoder's input")
+        e2e = {"ms": ms, "groups": ngroups, "tm": tm_e2e, "cap": cap}
+    e2e_pg = None
+    if args.e2e_pageable_steps > 0:
+        avail = mem_available()
+        cap = min(total + 4096, max(1 << 30, int(avail * 0.30) // (world if world > 1 else 1)))
+        if args.e2e_buffer_gb > 0:
+            cap = min(cap, int(args.e2e_buffer_gb * (1 << 30)))
+        staged_pg = Staged(corpus, pinned=False)
+        ms, ngroups, _, ok_e = e2e_leg(dec, staged_pg, pieces, args.e2e_pageable_steps, 1, barrier, False, cap)
+        if not ok_e:
+            raise SystemExit(f"bench.py: rank {rank}: end-to-end (pageable) PCM differs from the encoder's input")
+        e2e_pg = {"ms": ms, "groups": ngroups}
+    dec.close()
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
-    tm_e2e = dec.timing()
-
-    # ---- max over ranks ----------------------------------------------------------------
-    vec = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(samples), float(launches)], dtype=torch.float64, device="cuda")
+    # ---- max over ranks ---------------------------------------------------------------------------------
+    vec = torch.tensor([dev_ms, wall_ms, e2e["ms"] if e2e else 0.0, e2e_pg["ms"] if e2e_pg else 0.0],
+                       dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(samples), float(launches), float(n_frames), float(pcm_bytes), float(comp_bytes)],
+                       dtype=torch.float64, device="cuda")
+    ranges = torch.zeros(world * 2, dtype=torch.float64, device="cuda")
+    # this rank's global frame range (for the line's evidence that the shards differ)
     if world > 1:
+        first = sum(corpus.track(j).n_frames for j in range(pieces[0].j)) + pieces[0].f_lo if pieces else 0
+        ranges[2 * rank], ranges[2 * rank + 1] = float(first), float(first + n_frames)
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max, e2e_ms_max = (float(x) for x in vec.tolist())
-    samples_all, launches_all = (float(x) for x in tot.tolist())
+        dist.all_reduce(ranges, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, e2e_ms_max, e2e_pg_ms_max = (float(x) for x in vec.tolist())
+    samples_all, launches_all, frames_all, pcm_all, comp_all = (float(x) for x in tot.tolist())
 
     if rank == 0:
         peak, peak_src = measured_peak()
         stage = {k: acc[k] / args.steps for k in acc}
         b_alg = comp_bytes + pcm_bytes
-        fused = not (args.no_fusion or (args.flags & 2))
-        pack_fused = fused and bool(args.flags & 0x20) and not (args.flags & 4)
-        names = {"entropy_ms": ("k123_decode (fused entropy + LPC + pack)" if pack_fused else
-                                "k12_entropy_lpc (fused entropy + LPC)") if fused else "k1_entropy",
-                 "lpc_ms": "k2_lpc", "stereo_ms": "k3_stereo_pack"}
-        dom = max(("entropy_ms", "lpc_ms", "stereo_ms"), key=lambda k: stage[k])
-        path_ms = stage["kernels_ms"]        # whole pipeline, K0 included (stage["index_ms"] is its K0 part)
-        # dominant kernel: algorithmic bytes one launch is responsible for (the whole batch's compressed
-        # bytes in + PCM bytes out; intermediates not counted) / its CUDA-event duration
-        achieved = b_alg / (stage[dom] * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get(names[dom].split(" ")[0])
-        except Exception:
-            pass
+        frame_lanes = (not (args.flags & 0x42)) and ((args.flags & 0x80) or n_frames // max(1, len(devices)) >= 65536)
+        fused = not (args.flags & 2)
+        if frame_lanes:
+            dom_name, dom_sum = "kf_frames", stage["entropy_ms"] + stage["lpc_ms"]
+            dom_what = ("kf_frames<A> + kf_frames<B> (frame-lane entropy + LPC + un-mix/pack, the two phases of one "
+                        "kernel template; the class sort in front of phase A is inside the event pair)")
+        else:
+            key = max(("entropy_ms", "lpc_ms", "stereo_ms"), key=lambda k: stage[k])
+            dom_name = {"entropy_ms": "k12_entropy_lpc" if fused else "k1_entropy", "lpc_ms": "k2_lpc",
+                        "stereo_ms": "k3_stereo_pack"}[key]
+            dom_sum, dom_what = stage[key], dom_name
+        stage_sum = stage["index_ms"] + stage["entropy_ms"] + stage["lpc_ms"] + stage["stereo_ms"]
+        path_ms = stage["kernels_ms"]
+        share = dom_sum / max(stage_sum, 1e-9)
+        # chunks run concurrently on several streams, so per-launch event times overlap: the kernel's time is its
+        # share of the summed stage times applied to the pipeline's span (first launch -> last kernel done)
+        dom_ms = path_ms * share if chunks > 1 else dom_sum
+        achieved = b_alg / (dom_ms * 1e-3) / 1e9
+        traffic = load_profile_json("traffic.json").get(name, {}).get(dom_name)
+        issue = load_profile_json("issue.json").get(name, {}).get(dom_name)
         line = {
             "metric": METRIC, "value": samples_all / (wall_ms_max * 1e-3) / 1e6, "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": wall_ms_max,
+            "n_gpus": world if world > 1 else len(devices), "steps": args.steps, "warmup": warm, "ms_per_step": wall_ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "config": {
-                "workload": desc, "scale": args.scale, "frames_per_gpu": n_frames,
-                "samples_per_gpu": samples, "compressed_bytes_per_gpu": comp_bytes, "pcm_bytes_per_gpu": pcm_bytes,
-                "compression_ratio": comp_bytes / max(1, pcm_bytes),
-                "l2": "inputs + intermediates + PCM per step exceed the 126 MB L2 (no flush needed)"
-                      if b_alg > 2 * 126e6 else "working set below 2x L2: numbers include L2 hits",
-                "parallelism": f"frame-range shards, {world} rank(s), no collective",
-                "parity": "bit-exact vs encoder input and device checksum, checked in this run",
-                "fused_entropy_lpc": fused,
-                "numa_bind": numa,
+                "workload": corpus.desc, "scale": args.scale, "tracks": corpus.n_tracks,
+                "frames": int(frames_all), "samples": int(samples_all), "compressed_bytes": int(comp_all), "pcm_bytes": int(pcm_all),
+                "frames_rank0": n_frames, "compression_ratio": comp_all / max(1.0, pcm_all),
+                "l2": "inputs + PCM per step exceed the 126 MB L2 many times over (no flush needed)"
+                      if b_alg > 4 * 126e6 else "working set below 4x L2: numbers include L2 hits",
+                "parallelism": (f"frame-range shards of ONE batch over {world} ranks (alacgpu_plan_partition / shard.rank_slices), "
+                                "no data-path collective" if world > 1 else
+                                (f"one alacgpu context over {len(devices)} GPUs (in-library frame-range partition)" if single
+                                 else "1 GPU, one decode_all call")),
+                "rank_frame_ranges": [[int(ranges[2 * r]), int(ranges[2 * r + 1])] for r in range(world)] if world > 1 else None,
+                "parity": "per rank, before timing: device checksum of the decoded PCM == checksum of the encoder's input, every "
+                          "frame status OK; after the last timed step the checksum again; end-to-end legs byte-compared",
+                "decode_path": "frame lanes (kf_frames)" if frame_lanes else ("fused entropy + LPC (k12)" if fused else "k1 + k2 + k3"),
+                "setup_s": t_setup, "numa_bind": numa, "chunks_per_step": chunks,
             },
             "device_ms_per_step": dev_ms_max,
             "stage_ms": stage,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "e2e": {"value": samples_all / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": int(comp_bytes + 4 * n_frames) * world, "d2h_bytes_per_step": int(pcm_bytes) * world,   # whole job
-                    "ms_per_step": e2e_ms_max, "steps": args.e2e_steps,
-                    "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"], "pipeline_ms": tm_e2e["kernels_ms"],
-                    "api_ms": tm_e2e["total_ms"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": names[dom],
-                         "scope": "dominant kernel: algorithmic bytes (compressed in + PCM out of the batch, "
-                                  "intermediates not counted) / its average launch duration from CUDA events on "
-                                  "its launch stream (the event pair also spans the work-list sort and the plane clear in "
-                                  "front of it, ~0.1 ms); serial-dependency / ALU-issue bound, see DESIGN.md section 3",
-                         "dominant_kernel_ms": stage[dom], "dominant_kernel_share": stage[dom] / max(path_ms, 1e-9),
-                         "algorithmic_bytes": b_alg,
+                         "kernel": dom_what,
+                         "scope": "dominant kernel on rank 0: algorithmic bytes of the batch (compressed in + PCM out, "
+                                  "intermediates not counted) / its launch time from CUDA events on its launch streams "
+                                  "(summed over chunks; chunks overlap on several streams, so the sum is scaled to the "
+                                  "pipeline span by the kernel's share); the path is integer-issue bound, see `issue`",
+                         "dominant_kernel_ms": dom_ms, "dominant_kernel_ms_summed": dom_sum, "dominant_kernel_share": share,
+                         "algorithmic_bytes": b_alg, "issue": issue,
                          "whole_path": {"ms": path_ms, "achieved": b_alg / (path_ms * 1e-3) / 1e9,
                                         "frac": b_alg / (path_ms * 1e-3) / 1e9 / peak}},
         }
-        if world == 1 and args.batch_tracks > 0:
-            line["batch"] = batch_leg(args, local)
+        if e2e:
+            tm_e = e2e["tm"]
+            line["e2e"] = {"value": samples_all / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
+                           "h2d_bytes_per_step": int(comp_all + 4 * frames_all), "d2h_bytes_per_step": int(pcm_all),   # whole job
+                           "ms_per_step": e2e_ms_max, "steps": args.e2e_steps, "decode_all_calls_per_step": e2e["groups"],
+                           "host_buffers": "page-locked (alacgpu_host_alloc)", "host_out_buffer_bytes": e2e["cap"],
+                           "last_call": {k: tm_e[k] for k in ("h2d_ms", "d2h_ms", "kernels_ms", "total_ms")}}
+        if e2e_pg:
+            line["e2e_pageable"] = {"value": samples_all / (e2e_pg_ms_max * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_pg_ms_max,
+                                    "steps": args.e2e_pageable_steps, "decode_all_calls_per_step": e2e_pg["groups"],
+                                    "host_buffers": "plain pageable memory (numpy) for both mdat and PCM"}
+        if world == 1 and not single and args.latency_steps > 0 and name == "config4":
+            line["latency_legs"] = {k: latency_leg(k, args, local) for k in ("config1", "config2", "config3")}
         if not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v, sample, _ = cpu_decode_rate(tracks, max(8, min(2048, tracks[0].n_frames // cores)), cores, repeats=2)
-            v1, _, _ = cpu_decode_rate(tracks, 256, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            cores = host_cores()
+            _, _, dt0 = cpu_decode_rate(corpus, 8, cores)
+            per = int(max(8, min(2048, 12.0 / max(dt0 / 8.0, 1e-6))))
+            v, sample, _ = cpu_decode_rate(corpus, per, cores, repeats=2)
+            v1, _, _ = cpu_decode_rate(corpus, max(8, per // 4), 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": sample + "; oracle/ C restatement (C# reference not runnable here)",
                                     "one_core_value": v1}
         print(json.dumps(line), flush=True)
-    dec.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -431,19 +690,26 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2")
-    ap.add_argument("--scale", type=float, default=1.0, help="duration scale of the workload (1.0 = BASELINE config)")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--workload", default="auto", help="auto (N=1: config4 = configs[3]; N>1: config5 = configs[4]) | config1..config5")
+    ap.add_argument("--scale", type=float, default=1.0, help="duration scale of the tracks (1.0 = BASELINE config)")
+    ap.add_argument("--tracks", type=int, default=0, help="tracks of config4 / config5 (0 = 1000 / 1250 per GPU)")
+    ap.add_argument("--tracks-per-gpu", type=int, default=0)
+    ap.add_argument("--unique", type=int, default=8, help="distinct tracks generated for config4")
+    ap.add_argument("--unique-per-kind", type=int, default=1, help="distinct tracks per i mod 10 residue for config5")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-pageable-steps", type=int, default=2)
+    ap.add_argument("--e2e-buffer-gb", type=float, default=0.0, help="cap of the host PCM buffer of the e2e legs (0 = what fits)")
+    ap.add_argument("--latency-steps", type=int, default=20, help="steps of the configs[0..2] latency legs at N=1 (0 = skip)")
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--entropy-lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--flags", type=int, default=0, help="ALACGPU_FLAG_* bits: 2 no fusion, 4 no pack fusion, 8 no zero-copy output")
+    ap.add_argument("--flags", type=int, default=0,
+                    help="ALACGPU_FLAG_* bits: 2 no fusion, 4 no pack fusion, 8 no zero-copy output, 0x40 no frame lanes, 0x80 force frame lanes")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
-    ap.add_argument("--batch-tracks", type=int, default=64, help="tracks of the configs[3]-shaped throughput leg (0 = skip)")
-    ap.add_argument("--no-fusion", action="store_true", help="entropy and LPC as two kernels (A/B against the fused launch)")
+    ap.add_argument("--single-process", action="store_true", help="one process, ONE alacgpu context over --gpus devices")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

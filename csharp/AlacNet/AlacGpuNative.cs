@@ -29,7 +29,7 @@ namespace ALACdotNET.Decoder.Gpu
     internal enum AlacGpuFlags : uint
     {
         None = 0, KeepDevicePcm = 0x1, NoFusion = 0x2, NoPackFusion = 0x4, NoZeroCopy = 0x8,
-        NoQuadLpc = 0x10, ForcePackFusion = 0x20
+        NoQuadLpc = 0x10, ForcePackFusion = 0x20, NoFrameLanes = 0x40, ForceFrameLanes = 0x80
     }
 
     [StructLayout(LayoutKind.Sequential)]

@@ -94,16 +94,21 @@ enum {
 typedef struct alacgpu_ctx alacgpu_ctx;
 
 /* ---- options ------------------------------------------------------------- */
-/* Launch shapes (every combination yields the same bytes).  Default: one fused entropy + LPC launch per
- * chunk (LPC warps consume residuals while the entropy lanes still produce them) followed by the un-mix /
- * pack kernel; when the inputs are resident and pcm_dst is page-locked, ONE launch with entropy, LPC and
- * pack roles that writes the PCM straight into the destination (no device PCM, no D2H stage). */
+/* Launch shapes (every combination yields the same bytes).  Small batches (fewer frames than the GPU has
+ * lanes): one fused entropy + LPC launch per chunk (LPC warps consume residuals while the entropy lanes still
+ * produce them) followed by the un-mix / pack kernel; when the inputs are resident and pcm_dst is page-locked,
+ * ONE launch with entropy, LPC and pack roles that writes the PCM straight into the destination (no device
+ * PCM, no D2H stage).  Big batches (>= 65536 frames per device): the frame-lane kernels -- one lane per frame
+ * and channel from bitstream to PCM, no residual / sample planes in HBM except a half-width copy of channel A
+ * of stereo frames. */
 #define ALACGPU_FLAG_KEEP_DEVICE_PCM 0x1u    /* keep decoded PCM resident in HBM after decode_all */
 #define ALACGPU_FLAG_NO_FUSION 0x2u          /* entropy, LPC and pack as three kernels */
 #define ALACGPU_FLAG_NO_PACK_FUSION 0x4u     /* never the launch with pack roles: un-mix / pack stays a separate kernel */
 #define ALACGPU_FLAG_NO_ZERO_COPY 0x8u       /* never write PCM straight into a page-locked destination; always device PCM + D2H copies */
 #define ALACGPU_FLAG_NO_QUAD_LPC 0x10u       /* one lane per stream for every LPC stream (no four-lane path for the tail-critical ones) */
 #define ALACGPU_FLAG_FORCE_PACK_FUSION 0x20u /* the launch with pack roles even when the PCM stays in HBM (tests / A-B runs) */
+#define ALACGPU_FLAG_NO_FRAME_LANES 0x40u    /* never the frame-lane kernels (one lane per frame and channel from bitstream to PCM), which big batches use by default */
+#define ALACGPU_FLAG_FORCE_FRAME_LANES 0x80u /* the frame-lane kernels for every chunk, however small (tests / A-B runs) */
 
 typedef struct alacgpu_opts {
     uint32_t struct_size;      /* sizeof(alacgpu_opts), for forward compatibility       */

@@ -4,6 +4,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+# OR-ed into the context flags of every _decode call: tests/test_gpu_frame_lanes.py re-runs the scenarios of
+# this file with ALACGPU_FLAG_FORCE_FRAME_LANES (0x80)
+_EXTRA_FLAGS = 0
+
 
 def _decode(tracks, dst=None, resident=False, **kw):
     """resident=False: decode_all streams the mdat in chunk by chunk (entropy + LPC fused, K3 apart);
@@ -12,6 +16,7 @@ def _decode(tracks, dst=None, resident=False, **kw):
     from alac.net_b200 import BatchDecoder
     if resident and "flags" not in kw:
         kw["flags"] = 0x20
+    kw["flags"] = kw.get("flags", 0) | _EXTRA_FLAGS
     with BatchDecoder(**kw) as dec:
         for t in tracks:
             dec.add_track(t.cfg, t.mdat, t.stsz)
