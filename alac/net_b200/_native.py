@@ -57,7 +57,7 @@ class Timing(C.Structure):
         ("index_ms", C.c_float), ("entropy_ms", C.c_float), ("lpc_ms", C.c_float), ("stereo_ms", C.c_float),
         ("kernels_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
         ("kernel_launches", C.c_uint32), ("chunks", C.c_uint32), ("compressed_bytes", C.c_uint64),
-        ("pcm_bytes", C.c_uint64), ("samples", C.c_uint64),
+        ("pcm_bytes", C.c_uint64), ("samples", C.c_uint64), ("internal_retries", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
     def as_dict(self):

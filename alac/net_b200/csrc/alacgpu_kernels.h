@@ -50,6 +50,7 @@ struct ChunkArgs {
     uint32_t *lpc_done;            // fused launch: predicted samples published per stream by the LPC lanes (2n entries, zeroed)
     uint32_t *pack_next;           // fused launch: next pack task (zeroed)
     uint8_t *lpc_flag;             // per stream: 1 if the stream is on the LPC work list (written by the sort)
+    uint32_t *faults;              // device counter of frames flagged FS_INTERNAL (the runtime then re-decodes unfused)
     // frame-lane path (kf_frame.cu): work lists of chunk-local frame slots, every class padded to whole warps
     uint32_t *kf_list;             // [0, kf_cap) phase A, [kf_cap, 2 kf_cap) phase B, [2 kf_cap, 2 kf_cap + n) pack-only frames
     uint32_t *kf_count;            // [0] phase A entries (padded), [1] phase B entries (padded), [2] pack-only frames;

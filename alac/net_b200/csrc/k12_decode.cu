@@ -115,7 +115,7 @@ __device__ __forceinline__ void pack_role(const ChunkArgs &a, uint8_t *stage /* 
             uint32_t avail = 0;
             bool stalled = false;
             wait_avail(word, need, avail, mine, stalled);
-            if (__any_sync(0xffffffffu, stalled) && lane == 0) a.desc[a.f0 + slot].status = FS_INTERNAL;
+            if (__any_sync(0xffffffffu, stalled) && lane == 0) { a.desc[a.f0 + slot].status = FS_INTERNAL; atomicAdd(a.faults, 1u); }
         }
         uint32_t w[12], nbytes = 0, cnt = 0;
         uint8_t *dst = nullptr;

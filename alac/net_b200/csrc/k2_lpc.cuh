@@ -419,7 +419,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
         else if (maxo <= 28) ALACGPU_LPC4(7);
         else ALACGPU_LPC4(8);
 #undef ALACGPU_LPC4
-        if (kPoll && active && stalled && (lane & 3) == 0) a.desc[f].status = FS_INTERNAL;
+        if (kPoll && active && stalled && (lane & 3) == 0) { a.desc[f].status = FS_INTERNAL; atomicAdd(a.faults, 1u); }
         return;
     }
 #define ALACGPU_LPC(MM) case MM: stalled = lpc_warp<MM, kPoll, kPublish>(row, n, nmax, rss, q, coef16, active, prog, done); break
@@ -433,7 +433,7 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
         default: break;
     }
 #undef ALACGPU_LPC
-    if (kPoll && active && stalled) a.desc[f].status = FS_INTERNAL;   // never expected: see wait_avail
+    if (kPoll && active && stalled) { a.desc[f].status = FS_INTERNAL; atomicAdd(a.faults, 1u); }   // never expected: see wait_avail
 }
 
 }  // namespace alacgpu

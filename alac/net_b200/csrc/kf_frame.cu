@@ -574,7 +574,7 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
         else if (i > (uint32_t)kMaxFrameSamples) status = FS_RUN_OVERFLOW;  // reference: IndexOutOfRange
         const uint32_t end_bit = start_bit + br.consumed();
         if (end_bit > ref.len * 8u) status = FS_OVERRUN;                    // the cursor is monotone
-        if (stuck) status = FS_INTERNAL;                                    // never expected
+        if (stuck) { status = FS_INTERNAL; atomicAdd(a.faults, 1u); }       // never expected
         if (!kB && stereo) a.bstart[slot] = end_bit;
         if (status != FS_OK) a.desc[f].status = status;
     }

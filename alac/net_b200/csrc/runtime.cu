@@ -70,12 +70,30 @@ struct DevBuf {
         cap = want;
         return cudaSuccess;
     }
+    // grow, keeping the first `keep` elements (the arena of a context whose earlier tracks stay resident)
+    cudaError_t reserve_keep(size_t n, size_t keep)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (!p || keep == 0) return reserve(n);
+        T *q = nullptr;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(q, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) { cudaFree(q); return e; }
+        cudaFree(p);
+        p = q;
+        cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
 struct HostTrack {
     alacgpu_track_cfg cfg;
-    const uint8_t *mdat;          // borrowed until the first prepare()/decode_all() returns
+    const uint8_t *mdat;          // borrowed until the track's bytes are in HBM (the first prepare() / decode_all()
+                                  // after the add); nulled then -- the library never goes back to host memory
+    bool staged = false;          // bytes are resident in the arena (single-device contexts keep them across later adds)
     uint64_t mdat_len;
     uint64_t first_frame_offset;
     uint64_t first_frame;         // index into the global frame list
@@ -110,6 +128,7 @@ struct Device {
     uint64_t f_lo = 0, f_hi = 0;
     DevBuf<uint8_t> arena;
     uint64_t arena_used = 0;
+    uint64_t arena_staged = 0;        // bytes [0, arena_staged) hold tracks whose host memory is no longer borrowed
     DevBuf<FrameRef> refs;
     DevBuf<TrackCfg> cfgs;
     DevBuf<FrameDesc> desc;
@@ -152,6 +171,7 @@ struct alacgpu_ctx {
     alacgpu_timing timing{};
     // stage timings of the last pipeline are read back from its CUDA events on demand (alacgpu_get_timing):
     // ~80 event queries are not on the caller's critical path
+    uint32_t internal_faults = 0;         // frames flagged FS_INTERNAL by the last pipeline (a hand-off that timed out)
     bool index_stale = false;             // alacgpu_reindex: K0 runs again inside the next decode_all
     bool timing_pending = false;
     bool tp_stage = false, tp_index = false, tp_decode = false, tp_d2h = false, tp_zc = false;
@@ -312,7 +332,7 @@ int32_t build_plan(alacgpu_ctx *ctx)
                 d.h_refs[f - d.f_lo] = r;
                 compressed += r.len;
             }
-            if (src_hi > src_lo) d.track_copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo});
+            if (src_hi > src_lo && !ht.staged) d.track_copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo});
             used = base + (src_hi - src_lo);
         }
         d.arena_used = used;
@@ -325,7 +345,7 @@ int32_t build_plan(alacgpu_ctx *ctx)
         } else {
             d.pcm_first = d.pcm_lo = d.pcm_hi = 0;
         }
-        CU(d.arena.reserve(used + kArenaTail));
+        CU(d.arena.reserve_keep(used + kArenaTail, d.arena_staged));
         CU(d.refs.reserve(std::max<uint64_t>(n_local, 1)));
         CU(d.cfgs.reserve(cfgs.size()));
         CU(d.desc.reserve(std::max<uint64_t>(n_local, 1)));
@@ -421,6 +441,7 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
     ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
     ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames + 1024u;
+    ca.faults = reinterpret_cast<uint32_t *>(d.scalars.p) + 1;
     {
         // four-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
         // streams from order 17 up (configs[1], final r1 kernels: 2.65 ms; from 25 up 2.61, from 21 up 3.24,
@@ -585,7 +606,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         else
             cudaGetLastError();
     }
-    if (zc) {                      // alignment gaps between tracks are zero bytes in the layout
+    if (pcm_dst && decode) {       // alignment gaps between tracks are zero bytes in the layout (copies skip them)
         uint64_t end = 0;
         for (const HostTrack &ht : ctx->tracks) {
             if (ht.pcm_off > end) memset(pcm_dst + end, 0, ht.pcm_off - end);
@@ -654,6 +675,7 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
     // ---- wait + timings --------------------------------------------------------
     const double t_issued = now_ms();
     double t_synced = 0;
+    uint32_t faults = 0;
     for (int g = 0; g < n_dev; g++) {
         Device &d = ctx->devs[g];
         if (d.f_hi == d.f_lo) continue;
@@ -663,13 +685,21 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
         if (stage) CU(cudaStreamSynchronize(d.st_h2d));
         t_synced = now_ms();
         if (stage || index) d.resident = true;
+        if (stage) d.arena_staged = d.arena_used;
         if (decode) { d.decoded = true; d.pcm_resident = !zc; }     // zero-copy output leaves no PCM in HBM
-        if (index) {
-            uint32_t mism = 0;
-            CU(cudaMemcpy(&mism, d.scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            if (mism) return fail(ctx, ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size");
+        if (index || decode) {
+            uint32_t sc[2] = {0, 0};                                   // [0] K0 size mismatches, [1] FS_INTERNAL frames
+            CU(cudaMemcpy(sc, d.scalars.p, sizeof sc, cudaMemcpyDeviceToHost));
+            if (sc[0]) return fail(ctx, ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size");
+            if (sc[1]) {
+                faults += sc[1];
+                CU(cudaMemset(reinterpret_cast<uint32_t *>(d.scalars.p) + 1, 0, sizeof(uint32_t)));
+            }
         }
     }
+    ctx->internal_faults = faults;
+    if (stage)                        // every byte is in HBM now: the host memory is no longer borrowed
+        for (HostTrack &ht : ctx->tracks) { ht.staged = true; ht.mdat = nullptr; }
     if (getenv("ALACGPU_HOST_TIMING"))
         fprintf(stderr, "[alacgpu] run_pipeline: issue %.3f ms, wait %.3f ms, after %.3f ms\n", t_issued - t_enter, t_synced - t_issued, now_ms() - t_synced);
     ctx->timing_pending = true;
@@ -814,6 +844,12 @@ static int32_t add_track_impl(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, co
     if (cfg->rice_kmodifier < 0 || cfg->rice_kmodifier > 31 || cfg->rice_history_mult < 0 || cfg->rice_history_mult > 255 ||
         cfg->rice_initial_history < 0 || cfg->rice_initial_history > 255)
         return fail(ctx, ALACGPU_ERR_UNSUPPORTED, "rice parameters outside one cookie byte / kmodifier 0..31");
+    if (ctx->devs.size() > 1)
+        for (const HostTrack &ht : ctx->tracks)
+            if (ht.staged)
+                return fail(ctx, ALACGPU_ERR_STATE, "a multi-device context cannot take more tracks once its tracks are staged "
+                                                    "(the partition would move frames whose host bytes are no longer borrowed): "
+                                                    "call alacgpu_clear_tracks first");
     HostTrack t{};
     t.cfg = *cfg;
     t.mdat = mdat;
@@ -872,7 +908,7 @@ int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx)
     ctx->total_pcm = 0;
     ctx->max_sf = 0;
     invalidate(ctx);
-    for (Device &d : ctx->devs) d.f_lo = d.f_hi = 0;
+    for (Device &d : ctx->devs) { d.f_lo = d.f_hi = 0; d.arena_staged = 0; }
     return ALACGPU_OK;
 }
 
@@ -947,9 +983,28 @@ int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap, uin
     uint32_t launches = 0;
     r = run_pipeline(ctx, !resident, reindex, true, pcm_dst, &launches);
     if (r) return r;
+    uint32_t retries = 0;
+    static const bool inject = getenv("ALACGPU_TEST_INJECT_INTERNAL") != nullptr;   // tests: exercise the retry below
+    if (inject) ctx->internal_faults = 1;
+    if (ctx->internal_faults) {
+        // A consumer of a fused launch gave up waiting for its producer (never expected: only a GPU that is
+        // time-sliced or single-stepped can starve a resident block that long).  The frames it flagged hold
+        // zeros; decode the batch again with three plain kernels that do not wait on each other, so the caller
+        // never gets a silently wrong frame.
+        const uint32_t saved = ctx->opts.flags;
+        ctx->opts.flags |= ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_FRAME_LANES;
+        uint32_t more = 0;
+        r = run_pipeline(ctx, false, true, true, pcm_dst, &more);
+        ctx->opts.flags = saved;
+        if (r) return r;
+        launches += more;
+        retries = 1;
+        if (ctx->internal_faults && !inject) return fail(ctx, ALACGPU_ERR_STATE, "internal: frames still flagged after the unfused retry");
+    }
     ctx->index_stale = false;
     fill_totals(ctx);
     ctx->timing.kernel_launches = ctx->index_launches + launches;
+    ctx->timing.internal_retries = retries;
     ctx->timing.total_ms = (float)(now_ms() - t0);
     if (getenv("ALACGPU_HOST_TIMING")) fprintf(stderr, "[alacgpu] decode_all %.3f ms\n", now_ms() - t0);
     for (size_t t = 0; t < ctx->tracks.size(); t++) {

@@ -1,5 +1,12 @@
 // alacnet.cpp -- see alacnet.hpp.  Host-only code: container parsing, table walking and
 // byte shuffling.  Every PCM byte comes out of libalacgpu.so (alacgpu_read_frame).
+//
+// This file is a BEHAVIOURAL TWIN of the reference's C# host (ALACDecoder/QTMovieT.cs, MyStream.cs,
+// AlacContext.cs:83-295, AlacNetNAudioAdapter/ALACFileReader.cs:89-126), not product logic: the shipped
+// host stays the reference's own C# over P/Invoke (csharp/).  The image has no .NET, so this
+// twin is what lets the parity tests drive libalacgpu.so exactly the way AlacContext / ALACFileReader would
+// (same method names, same loops, the reference's quirks kept on purpose).  It decodes nothing and is not
+// meant to grow.
 #include "alacnet.hpp"
 
 #include <algorithm>
@@ -511,13 +518,21 @@ int64_t ALACFileReader::Position() const { return (int64_t)ctx_->LastSampleNumbe
 
 void ALACFileReader::SetPosition(int64_t value)
 {
+    std::lock_guard<std::mutex> g(reposition_lock_);       // :68
     ctx_->SetPosition(value / fmt_.BlockAlign());
     leftovers_ = 0;
+}
+
+void ALACFileReader::Dispose()
+{
+    std::lock_guard<std::mutex> g(reposition_lock_);       // :121
+    ctx_->Dispose();
 }
 
 int ALACFileReader::Read(uint8_t *buffer, int offset, int count)
 {
     int bytes_read = 0;
+    std::lock_guard<std::mutex> g(reposition_lock_);       // :92
     while (bytes_read < count) {
         if (leftovers_ > 0) {
             const int to_copy = std::min(leftovers_, count - bytes_read);

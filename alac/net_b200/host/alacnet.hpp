@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -150,7 +151,7 @@ public:
     void SetPosition(int64_t value);                       // :66-73
     const WaveFormat &GetWaveFormat() const { return fmt_; }   // :79
     int Read(uint8_t *buffer, int offset, int count);      // :89-116
-    void Dispose() { ctx_->Dispose(); }                    // :118-126
+    void Dispose();                                        // :118-126
     AlacContext &context() { return *ctx_; }
 
 private:
@@ -159,6 +160,7 @@ private:
     int64_t length_ = 0;
     int leftovers_ = 0, buffer_offset_ = 0;
     std::vector<uint8_t> decompress_;
+    std::mutex reposition_lock_;                           // _repositionLock, :53: Read, the Position setter and Dispose exclude each other
 };
 
 }  // namespace alacnet

@@ -18,20 +18,21 @@ constexpr uint32_t cc(char a, char b, char c, char d)
 }
 
 // next box at `pos` inside [pos, limit); false when nothing parseable is left
+// (all comparisons are written so that a crafted 64-bit size cannot wrap: pos <= limit always holds)
 bool next_box(const uint8_t *f, uint64_t pos, uint64_t limit, Box &b)
 {
-    if (pos + 8 > limit) return false;
+    if (pos > limit || limit - pos < 8) return false;
     uint64_t size = be32(f + pos);
     b.type = be32(f + pos + 4);
     uint64_t hdr = 8;
     if (size == 1) {                       // 64-bit largesize
-        if (pos + 16 > limit) return false;
+        if (limit - pos < 16) return false;
         size = be64(f + pos + 8);
         hdr = 16;
     } else if (size == 0) {                // box runs to the end of its container
         size = limit - pos;
     }
-    if (size < hdr || pos + size > limit) return false;
+    if (size < hdr || size > limit - pos) return false;
     b.body = pos + hdr;
     b.end = pos + size;
     return true;
@@ -94,7 +95,7 @@ void parse_stsd(const uint8_t *f, const Box &b, Tables &t)
     }
 }
 
-void parse_stbl(const uint8_t *f, const Box &stbl, Tables &t)
+void parse_stbl(const uint8_t *f, const Box &stbl, Tables &t, const uint64_t file_len)
 {
     uint64_t pos = stbl.body;
     Box b;
@@ -110,6 +111,9 @@ void parse_stbl(const uint8_t *f, const Box &stbl, Tables &t)
             const uint32_t uniform = be32(p + 4);
             uint64_t n = be32(p + 8);
             if (uniform) {
+                // a uniform table costs no file bytes, so bound it by what the file could hold: every frame
+                // occupies `uniform` bytes of a file no longer than the box's container
+                n = std::min<uint64_t>(n, file_len / uniform + 1);
                 n = std::min<uint64_t>(n, 1u << 28);
                 t.sizes.assign((size_t)n, uniform);
             } else {
@@ -132,18 +136,18 @@ void parse_stbl(const uint8_t *f, const Box &stbl, Tables &t)
 }
 
 // descend moov/trak/mdia/minf/stbl; stop at the first track that carries an ALAC sample entry
-bool find_track(const uint8_t *f, uint64_t lo, uint64_t hi, int depth, Tables &t)
+bool find_track(const uint8_t *f, uint64_t lo, uint64_t hi, int depth, Tables &t, const uint64_t file_len)
 {
     uint64_t pos = lo;
     Box b;
     while (next_box(f, pos, hi, b)) {
         if (b.type == cc('s', 't', 'b', 'l')) {
             Tables cand;
-            parse_stbl(f, b, cand);
+            parse_stbl(f, b, cand, file_len);
             if (cand.have_alac) { t = std::move(cand); return true; }
         } else if (depth < 6 && (b.type == cc('m', 'o', 'o', 'v') || b.type == cc('t', 'r', 'a', 'k') ||
                                  b.type == cc('m', 'd', 'i', 'a') || b.type == cc('m', 'i', 'n', 'f'))) {
-            if (find_track(f, b.body, b.end, depth + 1, t)) return true;
+            if (find_track(f, b.body, b.end, depth + 1, t, file_len)) return true;
         }
         pos = b.end;
     }
@@ -155,7 +159,7 @@ bool find_track(const uint8_t *f, uint64_t lo, uint64_t hi, int depth, Tables &t
 bool IsoDemux(const uint8_t *file, size_t len, IsoTrack &out, std::string &err)
 {
     Tables t;
-    if (!find_track(file, 0, len, 0, t)) { err = "no ALAC audio track found"; return false; }
+    if (!find_track(file, 0, len, 0, t, len)) { err = "no ALAC audio track found"; return false; }
     const size_t n = t.sizes.size();
     out.cfg = t.cfg;
     out.sizes = t.sizes;

@@ -61,6 +61,7 @@ namespace ALACdotNET.Decoder.Gpu
         public float IndexMs, EntropyMs, LpcMs, StereoMs, KernelsMs, H2dMs, D2hMs, TotalMs;
         public uint KernelLaunches, Chunks;
         public ulong CompressedBytes, PcmBytes, Samples;
+        public uint InternalRetries, Reserved;
     }
 
     internal sealed class AlacGpuHandle : SafeHandle

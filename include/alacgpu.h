@@ -60,7 +60,7 @@ extern "C" {
 #define ALACGPU_API __attribute__((visibility("default")))
 #endif
 
-#define ALACGPU_ABI_VERSION 1
+#define ALACGPU_ABI_VERSION 2
 
 /* ---- call status -------------------------------------------------------- */
 enum {
@@ -113,7 +113,9 @@ typedef struct alacgpu_ctx alacgpu_ctx;
 typedef struct alacgpu_opts {
     uint32_t struct_size;      /* sizeof(alacgpu_opts), for forward compatibility       */
     uint32_t flags;            /* ALACGPU_FLAG_*                                         */
-    uint32_t chunk_frames;     /* frames per pipeline chunk (0 = default 32768)          */
+    uint32_t chunk_frames;     /* frames per pipeline chunk; 0 = automatic: resident inputs, as many frames as the
+                                  launch shape takes (32768, frame-lane kernels 262144); inputs streamed in from
+                                  the host, 1/16 of the device's frames (>= 256) so copies and kernels overlap */
     uint32_t entropy_lanes;    /* frames per entropy warp: 0 = auto, or 8 / 16 / 32      */
     uint32_t reserved[4];
 } alacgpu_opts;
@@ -147,6 +149,9 @@ typedef struct alacgpu_timing {
     uint64_t compressed_bytes; /* sum of stsz over all frames                    */
     uint64_t pcm_bytes;        /* PCM bytes produced                             */
     uint64_t samples;          /* channel values produced (sample-frames x container channels) */
+    uint32_t internal_retries; /* 1 if the batch was decoded a second time with unfused kernels because a fused
+                                  launch flagged ALACGPU_FRAME_INTERNAL (never expected; see alacgpu_decode_all) */
+    uint32_t reserved;
 } alacgpu_timing;
 
 /* ---- context ------------------------------------------------------------- */
@@ -166,8 +171,12 @@ ALACGPU_API int32_t alacgpu_destroy(alacgpu_ctx *ctx);
  * addressing (AlacContext.cs:194-195).  Frames that extend past mdat_len are
  * truncated (short read, MyStream.cs:47-52).  Only the frame headers are
  * looked at during this call; the bytes are copied to HBM by alacgpu_prepare or
- * by the first alacgpu_decode_all, so `mdat` must stay valid until that call
- * returns (frame_sizes is copied immediately). */
+ * by the first alacgpu_decode_all after the add, so `mdat` must stay valid until
+ * that call returns (frame_sizes is copied immediately).  Once that call has
+ * returned the library never reads `mdat` again: tracks added later are staged on
+ * their own and the earlier ones stay resident in HBM (single-device contexts; a
+ * multi-device context refuses new tracks after staging with ALACGPU_ERR_STATE,
+ * because its partition would have to move frames -- alacgpu_clear_tracks first). */
 ALACGPU_API int32_t alacgpu_add_track(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg,
                                       const uint8_t *mdat, uint64_t mdat_len,
                                       uint64_t first_frame_offset,
@@ -211,9 +220,13 @@ ALACGPU_API int32_t alacgpu_reindex(alacgpu_ctx *ctx);
  * optional) receive where each track's interleaved little-endian PCM landed;
  * frame_status (one int32 per frame, track-major, optional) receives the
  * ALACGPU_FRAME_* codes.  If the tracks are not resident yet (no
- * alacgpu_prepare) the call runs the whole pipeline: pinned/pageable H2D of
- * each chunk's mdat -> K0 -> K1 -> K2 -> K3 -> D2H of the chunk's PCM, with
- * up to 8 chunks in flight on separate CUDA streams. */
+ * alacgpu_prepare) the call runs the whole pipeline: H2D of each chunk's mdat
+ * -> header pre-pass -> decode kernels -> D2H of the chunk's PCM, with up to 16
+ * chunks in flight on separate CUDA streams (3 for the frame-lane kernels, whose
+ * chunks fill the machine on their own).  A frame the kernels flag
+ * ALACGPU_FRAME_INTERNAL (a fused launch's hand-off timed out) is never returned
+ * as zeros: the call decodes the batch again with unfused kernels first
+ * (alacgpu_timing.internal_retries). */
 ALACGPU_API int32_t alacgpu_decode_all(alacgpu_ctx *ctx, uint8_t *pcm_dst, uint64_t cap,
                                        uint64_t *track_pcm_off, uint64_t *track_pcm_len,
                                        int32_t *frame_status);

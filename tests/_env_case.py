@@ -26,6 +26,8 @@ def main():
                 if resident:
                     dec.prepare()
                 pcm, off, ln, status = dec.decode_all()
+                if os.environ.get("ALACGPU_TEST_INJECT_INTERNAL"):
+                    assert dec.timing()["internal_retries"] == 1, "the unfused retry did not run"
             pos = 0
             for t, o_, l_ in zip(tracks, off, ln):
                 ref, st, _ = oracle.decode_track(oracle.cfg_from(t.cfg), t.mdat, t.stsz)

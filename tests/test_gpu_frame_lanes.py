@@ -70,6 +70,11 @@ def test_empty_and_ragged_inputs(gen, oracle):
         assert out[int(off[1]):int(off[1] + ln[1])].tobytes() == ref
 
 
+def test_tracks_added_after_a_decode(gen, oracle):
+    P.test_tracks_added_after_a_decode_never_go_back_to_host_memory(gen, oracle)
+    P.test_pageable_destination_gets_zero_gaps(gen, oracle)
+
+
 @pytest.mark.parametrize("seed", range(2))
 def test_random_payload_fuzz(seed, gen, oracle):
     from tests.test_fuzz_oracle_model import random_frame

@@ -369,6 +369,7 @@ def test_two_devices_in_one_context(gen, oracle):
     {"ALACGPU_QUAD_MIN_LAST": "3", "ALACGPU_QUAD_MIN_FIRST": "3"},      # four-lane LPC for (almost) every stream: T = 2..8
     {"ALACGPU_QUAD_MIN_LAST": "9", "ALACGPU_QUAD_MIN_FIRST": "13"},
     {"ALACGPU_QUAD_MIN_LAST": "0", "ALACGPU_QUAD_MIN_FIRST": "0", "ALACGPU_NO_TAPER": "1"},   # one lane per stream only
+    {"ALACGPU_TEST_INJECT_INTERNAL": "1"},      # pretend a fused hand-off timed out: the batch is decoded again unfused
 ])
 def test_tuning_environment_does_not_change_bytes(env):
     """The four-lane LPC thresholds and the chunk taper are per-process environment knobs."""
@@ -412,3 +413,48 @@ def test_random_payload_fuzz_matches_oracle(seed, gen, oracle):
         got, status, _ = _decode(tracks, flags=flags, resident=resident)
         _assert_tracks_equal(tracks, got, status, oracle, check_encoder=False)
         assert (status == 0).any() and (status != 0).any()
+
+
+def test_tracks_added_after_a_decode_never_go_back_to_host_memory(gen, oracle):
+    """alacgpu.h: `mdat` is borrowed until the first prepare / decode_all after the add returns.  A track added
+    AFTER that is staged on its own; the earlier tracks stay resident in HBM even though the caller has reused
+    their buffers (the re-plan used to re-copy every earlier track from its stale host pointer)."""
+    from alac.net_b200 import BatchDecoder
+    ta = gen.make_config(1, scale=0.05)[0]
+    tb = gen.make_config(2, scale=0.01)[0]
+    tc = gen.make_config(3, scale=0.05)[0]
+    refs = [_oracle(oracle, t)[0] for t in (ta, tb, tc)]
+    with BatchDecoder(devices=[0], flags=_EXTRA_FLAGS) as dec:
+        a = np.frombuffer(ta.mdat, np.uint8).copy()
+        dec.add_track(ta.cfg, a, ta.stsz)
+        out, off, ln, _ = dec.decode_all()
+        assert out[int(off[0]):int(off[0] + ln[0])].tobytes() == refs[0]
+        a[:] = 0xA5                                       # the caller's buffer is its own again
+        b = np.frombuffer(tb.mdat, np.uint8).copy()
+        dec.add_track(tb.cfg, b, tb.stsz)
+        dec.prepare()
+        b[:] = 0x5A
+        c = np.frombuffer(tc.mdat, np.uint8).copy()
+        dec.add_track(tc.cfg, c, tc.stsz)
+        out, off, ln, status = dec.decode_all()
+        assert (status == 0).all()
+        for r, o, l in zip(refs, off, ln):
+            assert out[int(o):int(o + l)].tobytes() == r
+        assert dec.read_frame(0, 2) == refs[0][2 * 16384:3 * 16384]
+
+
+def test_pageable_destination_gets_zero_gaps(gen, oracle):
+    """the 256-byte alignment gaps between tracks are zero bytes in a pageable destination too (copy path)"""
+    from alac.net_b200 import BatchDecoder
+    tracks = gen.make_config(1, scale=0.013) + gen.make_config(3, scale=0.017) + gen.make_config(2, scale=0.003)
+    with BatchDecoder(devices=[0], flags=_EXTRA_FLAGS, chunk_frames=32) as dec:
+        for t in tracks:
+            dec.add_track(t.cfg, t.mdat, t.stsz)
+        total = dec.total_pcm_bytes()
+        dst = np.full(total, 0xAB, dtype=np.uint8)
+        out, off, ln, status = dec.decode_all(dst)
+        ends = [int(o + l) for o, l in zip(off, ln)]
+        starts = [int(o) for o in off[1:]] + [total]
+        assert any(s > e for e, s in zip(ends, starts))
+        for e, s in zip(ends, starts):
+            assert not out[e:s].any()

@@ -55,7 +55,7 @@ def test_csharp_binding_declares_every_symbol_and_flag():
 def test_library_loads_and_answers_without_a_gpu(built):
     from alac.net_b200 import _native as N
     L = N.load()
-    assert L.alacgpu_abi_version() == 1
+    assert L.alacgpu_abi_version() == 2
     assert L.alacgpu_strerror(0) == b"ok"
     assert b"no CPU fallback" in L.alacgpu_strerror(N.ERR_NAMES and -2)
     n = C.c_int32(-1)
@@ -240,3 +240,30 @@ def test_wav_header_fields(built):
     data, = struct.unpack("<I", h[40:44])
     assert (fmt_len, tag, ch, rate, bps, align, bits) == (16, 1, 2, 96000, 96000 * 6, 6, 24)
     assert data == 345_600_000 and riff == data + 36
+
+
+def test_iso_demux_survives_crafted_sizes(built, gen):
+    """A 64-bit box size near 2^64 must not wrap the bounds check (next_box), and a uniform stsz must
+    not allocate more entries than the file could hold: the demuxer answers (or refuses) without reading
+    outside the buffer."""
+    import struct
+    from alac.net_b200 import hostmirror as H
+    t = gen.make_config(1, scale=0.02)[0]
+    m4a = bytearray(gen.mux_m4a_ex(t))
+    at = bytes(m4a).find(b"sgpd") - 4                     # an ignorable box inside stbl, 8 + 12 bytes
+    assert at > 0
+    for largesize in (0xFFFFFFFFFFFFFFF0, 0xFFFFFFFFFFFFFFFF - at, 1 << 63, 17):
+        bad = bytearray(m4a)
+        bad[at:at + 4] = struct.pack(">I", 1)
+        bad[at + 8:at + 16] = struct.pack(">Q", largesize)
+        try:
+            d = H.iso_demux(bytes(bad))
+            assert d["stsz"].size <= t.n_frames
+        except H.IOException:
+            pass
+    # uniform stsz: sample_size != 0, absurd count
+    plain = bytearray(gen.mux_m4a(t))
+    s = bytes(plain).find(b"stsz") + 4
+    plain[s + 4:s + 12] = struct.pack(">II", 4096, 0xFFFFFFFF)
+    d = H.iso_demux(bytes(plain))
+    assert d["stsz"].size <= len(plain) // 4096 + 1
