@@ -259,7 +259,7 @@ struct PlaneRing {
 
 // ---- one entropy step with the residual left in a register ------------------------------------------
 // k1_entropy.cuh's ALACGPU_ENTROPY_STEP with three changes: a lane that still holds an unconsumed
-// residual (%15 have) sits the step out; a completed value goes to %16 instead of a plane; a completed
+// residual (%15 have) or owes zeros of a run (%14 pend) sits the step out; a completed value goes to %16 instead of a plane; a completed
 // zero-run length becomes %14 = the number of zero residuals still to hand out (clipped to the frame)
 // while the symbol index jumps as before.  Operands:
 //   %0 cur %1 nxt %2 nn %3 off %4 wpos | %5 i %6 nc %7 h %8 smm1 %9 kk %10 mk %11 mm %12 R %13 W
@@ -289,7 +289,8 @@ struct PlaneRing {
     "add.u32 rawv, rawv, 1;\n\t"                                                                          \
     "selp.u32 dv, rawv, rice, pW;\n\t"                                                                    \
     "setp.lt.u32 pA, %5, %6;\n\t"                                                                         \
-    "setp.eq.and.u32 pA, %15, 0, pA;\n\t"              /* a lane with a residual in hand waits */         \
+    "setp.eq.and.u32 pA, %15, 0, pA;\n\t"              /* a lane with a residual in hand waits, */        \
+    "setp.eq.and.u32 pA, %14, 0, pA;\n\t"              /* and so does one that still owes zeros of a run */ \
     "not.pred nA, pA;\n\t"                                                                                \
     "sub.u32 alt, 32, rsh;\n\t"                                                                           \
     "selp.u32 alt, alt, 9, pW;\n\t"                                                                       \

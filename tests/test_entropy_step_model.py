@@ -46,9 +46,15 @@ class _Window:
         return ((self.value & ((1 << have) - 1)) << (32 - have)) & U32 if have else 0
 
 
-def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_escape=False):
+def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_escape=False, lane_mode=False, consume=None):
     """Drop-in for alac_model.rice_decode built from the kernel's step.  `mask` is the run-length
-    multiplier mask (1 << kmod) - 1 the model passes for the zero-run symbol (AlacFile.cs:236)."""
+    multiplier mask (1 << kmod) - 1 the model passes for the zero-run symbol (AlacFile.cs:236).
+
+    lane_mode: the variant of the frame-lane kernels (kf_frame.cu, ALACGPU_ENTROPY_STEP_F): the residual stays in
+    a register (`have`, `e`) until the predictor of the same lane consumes it -- which happens only in rounds
+    where every lane of the warp has one, modelled by `consume(round) -> bool` -- a lane holding a residual
+    (or still owing zeros of a run) sits the step out, and a zero run becomes `pend` zero residuals handed out one per round (clipped to the
+    frame) while the symbol index jumps as before."""
     assert mask == (1 << kmod) - 1
     win = _Window(br)
     out = [0] * n                                   # the cleared plane row
@@ -61,7 +67,19 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
     mm = mk
     run, raw = False, False
     steps = 0
-    while i < nc:
+    have, pend, e_reg, j, rounds = False, 0, 0, 0, 0
+    while i < nc or (lane_mode and (have or pend)):
+        if lane_mode:
+            rounds += 1
+            assert rounds <= 16 * n + 64
+            if have or pend or i >= nc:             # the lane sits this step out: nothing of its state moves
+                if not have and pend:
+                    have, e_reg, pend = True, 0, pend - 1
+                if have and (consume is None or consume(rounds)):
+                    out[j] = e_reg
+                    j += 1
+                    have = False
+                continue
         steps += 1
         assert steps <= 4 * n, "at most four steps per sample: value and run length, each with its raw field"
         w = win.peek()
@@ -89,18 +107,22 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
         cons &= U32
         assert cons <= 32, "a step moves the cursor by at most one word"
         win.pos += cons
-        pend = esc and not raw and not fused_esc
-        is_val = not pend and not run
-        is_run = not pend and run
+        pend_raw = esc and not raw and not fused_esc
+        is_val = not pend_raw and not run
+        is_run = not pend_raw and run
         hb = _s32(h - (_s32(h * mult) >> 9))
         hn = _s32(dv * mult + hb)
         if dv > 0xFFFF:
             hn = 0xFFFF
         isum = (i + dv) & U32
         if is_val:
-            out[i] = _s32((dv >> 1) ^ (-(dv & 1) & U32))
+            if lane_mode:
+                have, e_reg = True, _s32((dv >> 1) ^ (-(dv & 1) & U32))
+            else:
+                out[i] = _s32((dv >> 1) ^ (-(dv & 1) & U32))
             i += 1
         if is_run:
+            pend = min(isum, nc) - i                # zeros of the run that lie inside the frame
             i = isum
         to_run = is_val and (hn & U32) < 128 and i < nc
         if is_val and hn < 0:
@@ -120,8 +142,17 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
         kk = kkz if to_run else (kk_after_run if is_run else kkv)
         mk = ((1 << ((kk + 1) & 31)) - 1) & U32        # shf.l.wrap(2, 2, kk) - 1
         mm = mk & (mask if to_run else U32)
-        run = run if pend else to_run
-        raw = pend
+        run = run if pend_raw else to_run
+        raw = pend_raw
+        if lane_mode:
+            if not have and pend:
+                have, e_reg, pend = True, 0, pend - 1
+            if have and (consume is None or consume(rounds)):
+                out[j] = e_reg
+                j += 1
+                have = False
+    if lane_mode:
+        assert j == n and not have and not pend, "every residual was handed out exactly once"
     br.pos = win.pos
     return out
 
@@ -204,3 +235,32 @@ def test_float_exponent_is_floor_log2_on_the_whole_domain():
         assert ex == (0 if v9 == 0 else 127 + v9.bit_length() - 1)
     for v in list(range(3, 70000)) + [(1 << 23) - 1, 1 << 22, (1 << 22) + 1]:
         assert _exp_of(0x4B000000 | v) == 127 + v.bit_length() - 1
+
+
+@pytest.mark.parametrize("idx", [0, 1, 3, 5, 9, 10])
+def test_frame_lane_variant_hands_out_every_residual_once(idx, gen, monkeypatch):
+    """kf_frame.cu: residual in a register until the lane's predictor takes it, zero runs as pending zeros,
+    a waiting lane's state frozen -- with the consumer (the warp-wide predictor round) arriving at irregular
+    intervals"""
+    ss, ch, kw = CASES[idx]
+    kw = dict(kw)
+    rng = np.random.default_rng(6000 + idx)
+    cfg = gen.TrackCfg(ss, ch, 256, kw.pop("hist_mult", 40), kw.pop("init_hist", 10), kw.pop("kmod", 14), 44100)
+    total = 256 * 4 + 31
+    x = gen.make_signal(int(rng.integers(1, 1 << 31)), total, ss, 44100, ch, wasted_spans=(ss == 24)).copy()
+    if kw.pop("loud", False):
+        lim = 1 << (ss - 1)
+        x[:, ::3] = rng.integers(-lim, lim, size=x[:, ::3].shape)
+    if kw.pop("quiet", False):
+        x[:] = 0
+        x[:, rng.integers(0, total, size=40)] = rng.integers(-3, 4, size=(ch, 40))
+    fr = gen.make_frames(rng, cfg, total, ch == 2, **kw)
+    if ss == 24:
+        gen.assign_wasted_bytes(fr, x, 24, rng)
+    t = gen.build_track(cfg, x, fr)
+    ck = M.Cookie(cfg.sample_size, cfg.num_channels, cfg.max_samples_per_frame, cfg.rice_history_mult,
+                  cfg.rice_initial_history, cfg.rice_kmodifier)
+    pattern = rng.integers(0, 3, size=997)
+    for consume in (None, lambda r: pattern[r % 997] == 0):
+        monkeypatch.setattr(M, "rice_decode", lambda *a: step_rice_decode(*a, lane_mode=True, consume=consume))
+        assert M.decode_track(ck, t.mdat, t.stsz) == t.pcm
