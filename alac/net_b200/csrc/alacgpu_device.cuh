@@ -75,6 +75,26 @@ struct __align__(16) FrameCoefs {
     int16_t c[2][32];
 };
 
+// ---- ALACGPU_CHECKED: bounds assertions (the stand-in for compute-sanitizer, which is closed on this GPU pool) --
+// Built with -DALACGPU_CHECKED (libalacgpu_checked.so) every index the kernels derive from stream contents is
+// compared with the extent of the buffer it goes into before it is used; a violation sets one bit of a device
+// word, the access is skipped, and the runtime fails the call with ALACGPU_ERR_STATE naming the bits.  The
+// release build compiles the checks away.
+enum : uint32_t {
+    CK_ARENA = 0,        // bitstream read outside the staged bytes + tail padding
+    CK_PLANE = 1,        // plane row / sample index outside the slot's planes
+    CK_LIST = 2,         // work-list / perm index outside the list
+    CK_PROGRESS = 3,     // progress / done word index outside the slot's words
+    CK_PCM = 4,          // PCM write outside the device's PCM buffer
+    CK_RING = 5,         // shared-memory ring over- or under-run
+    CK_FRAME = 6,        // frame index outside the chunk
+};
+#ifdef ALACGPU_CHECKED
+#define ALACGPU_CHECK(word, cond, code) ((cond) ? true : (atomicOr((word), 1u << (code)), false))
+#else
+#define ALACGPU_CHECK(word, cond, code) (true)
+#endif
+
 // ---- big-endian bit access into the arena --------------------------------
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 

@@ -23,6 +23,8 @@ struct K0Args {
     uint32_t *mismatch;           // incremented when K0's size differs from expect_len
     uint64_t f0;                  // first frame of this launch (device-local index)
     uint32_t n;
+    uint64_t arena_bytes;         // (ALACGPU_CHECKED) staged bytes + tail padding
+    uint32_t *check;              // (ALACGPU_CHECKED) violation word
 };
 cudaError_t launch_k0(const K0Args &a, cudaStream_t st, uint32_t *launches);
 
@@ -51,6 +53,11 @@ struct ChunkArgs {
     uint32_t *pack_next;           // fused launch: next pack task (zeroed)
     uint8_t *lpc_flag;             // per stream: 1 if the stream is on the LPC work list (written by the sort)
     uint32_t *faults;              // device counter of frames flagged FS_INTERNAL (the runtime then re-decodes unfused)
+    // extents for the ALACGPU_CHECKED build (alacgpu_device.cuh); `check` is its violation word
+    uint32_t *check;
+    uint64_t arena_bytes;          // staged bytes + tail padding
+    uint64_t plane_bytes;          // bytes of this slot's planes
+    uint64_t pcm_bytes;            // bytes of the device PCM buffer (or of the mapped destination)
     // frame-lane path (kf_frame.cu): work lists of chunk-local frame slots, every class padded to whole warps
     uint32_t *kf_list;             // [0, kf_cap) phase A, [kf_cap, 2 kf_cap) phase B, [2 kf_cap, 2 kf_cap + n) pack-only frames
     uint32_t *kf_count;            // [0] phase A entries (padded), [1] phase B entries (padded), [2] pack-only frames;
@@ -74,7 +81,7 @@ cudaError_t launch_k3(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);
 constexpr uint32_t kKfClasses = 256;
 inline uint32_t kf_list_cap(uint32_t n) { return (n + kKfClasses * 31u + 31u) & ~31u; }
 inline size_t kf_list_words(uint32_t n) { return 2u * (size_t)kf_list_cap(n) + n; }
-constexpr size_t kKfCountWords = 8 + 4 * 3 * kKfClasses;
+constexpr size_t kKfCountWords = 3200;   // counts, class histograms / cursors and the per-SM schedule (kf_frame.cu)
 cudaError_t launch_kf_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);   // class sort -> work lists
 cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);      // phase A
 cudaError_t launch_kf_b(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);      // phase B

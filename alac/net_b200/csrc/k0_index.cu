@@ -124,10 +124,14 @@ __global__ void __launch_bounds__(128)
 k0_parse_headers(const uint8_t *__restrict__ arena, const FrameRef *__restrict__ refs,
                  const TrackCfg *__restrict__ cfgs, uint32_t n_frames,
                  FrameDesc *__restrict__ desc, FrameCoefs *__restrict__ coefs,
-                 const uint32_t *__restrict__ expect_len, uint32_t *__restrict__ mismatch)
+                 const uint32_t *__restrict__ expect_len, uint32_t *__restrict__ mismatch,
+                 const uint64_t arena_bytes, uint32_t *__restrict__ check)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
+#ifdef ALACGPU_CHECKED
+    if (!ALACGPU_CHECK(check, refs[f].off + refs[f].len <= arena_bytes, CK_ARENA)) return;
+#endif
     const uint32_t len = parse_one(f, arena, refs, cfgs, desc, coefs);
     if (len != expect_len[f]) atomicAdd(mismatch, 1u);   // host layout rule out of sync (never expected)
 }
@@ -138,7 +142,7 @@ cudaError_t launch_k0(const K0Args &a, cudaStream_t st, uint32_t *launches)
     if (a.n == 0) return cudaSuccess;
     const uint32_t nb = (a.n + 127) / 128;
     k0_parse_headers<<<nb, 128, 0, st>>>(a.arena, a.refs + a.f0, a.cfgs, a.n, a.desc + a.f0, a.coefs + a.f0,
-                                         a.expect_len + a.f0, a.mismatch);
+                                         a.expect_len + a.f0, a.mismatch, a.arena_bytes, a.check);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -109,6 +109,10 @@ struct BitCursor {
     uint32_t off;           // cursor bit within `cur`, 0..31
     uint32_t pos0;          // cursor at init, in bits from chunk 0
     uint32_t filled;        // chunks [0, filled) have been requested
+#ifdef ALACGPU_CHECKED
+    const uint8_t *lim;     // one past the last staged byte (incl. tail padding)
+    uint32_t *chk;
+#endif
 
     template <bool kCommit = true>
     __device__ __forceinline__ void top_up()
@@ -116,14 +120,23 @@ struct BitCursor {
         const uint32_t want = (wpos >> 2) + kAhead;
 #pragma unroll
         for (int j = 0; j < kTopUpMax; j++) {
-            const uint32_t go = filled < want ? 1u : 0u;
+            uint32_t go = filled < want ? 1u : 0u;
+#ifdef ALACGPU_CHECKED
+            if (go && !ALACGPU_CHECK(chk, base + ((uint64_t)filled << 4) + 16 <= lim, CK_ARENA)) go = 0u;
+#endif
             cp_async16_if(ring + ((filled & (kRingChunks - 1)) << 4), base + ((uint64_t)filled << 4), go);
             filled += go;
         }
         if (kCommit) cp_async_commit();
     }
-    __device__ __forceinline__ void init(const uint8_t *arena, uint64_t abs_bit, const uint8_t *ring_ptr)
+    __device__ __forceinline__ void init(const uint8_t *arena, uint64_t abs_bit, const uint8_t *ring_ptr,
+                                         const uint64_t arena_bytes = 0, uint32_t *check = nullptr)
     {
+#ifdef ALACGPU_CHECKED
+        lim = arena + arena_bytes;
+        chk = check;
+        if (!ALACGPU_CHECK(chk, (abs_bit >> 3) + 16u * (kAhead + 2) <= arena_bytes, CK_ARENA)) abs_bit = 0;
+#endif
         const uint64_t byte = abs_bit >> 3;
         base = arena + (byte & ~15ull);
         ring = (uint32_t)__cvta_generic_to_shared(ring_ptr);
@@ -298,6 +311,8 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     const uint64_t f = a.f0 + (work ? slot : 0u);
     const FrameDesc d = a.desc[f];
     work = work && d.status == FS_OK && !(d.flags & FF_ESCAPE) && d.n > 0;   // escape frames are read directly by K3
+    // (checked build) the lane's two plane rows lie inside the slot's planes
+    if (work && !ALACGPU_CHECK(a.check, ((uint64_t)slot * 2u + 2u) * a.ns * 4u <= a.plane_bytes && d.n <= a.ns, CK_PLANE)) work = false;
     const FrameRef ref = a.refs[f];
     const TrackCfg cfg = a.cfgs[ref.track];
     const uint32_t n = work ? (uint32_t)d.n : 0u;             // samples per channel
@@ -310,7 +325,8 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     const uint32_t kk0 = min(exp_of(0x4B000000u | (uint32_t)((h0 >> 9) + 3)), kcap);   // :221-222
 
     BitCursor br;
-    br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull, ring_smem + threadIdx.x * (uint32_t)kRingBytes);
+    br.init(a.arena, work ? ref.off * 8ull + d.data_bit : 0ull, ring_smem + threadIdx.x * (uint32_t)kRingBytes,
+            a.arena_bytes, a.check);
 
     // per-lane decode state
     uint32_t chans = work ? ((d.flags & FF_STEREO) ? 2u : 1u) : 0u;    // channels still to finish, the current one included

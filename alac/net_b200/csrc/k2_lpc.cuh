@@ -387,6 +387,11 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
     if (!quad && warp * 32u >= n_active) return;
     uint32_t sid = kNoStream;
     if (quad ? idx < n_quad : idx < n_active) sid = quad ? a.perm[quad_base(a.n) + idx] : a.perm[idx];
+    // (checked build) list sizes and stream ids inside the chunk, rows inside the planes
+    if (!ALACGPU_CHECK(a.check, n_active <= 2u * a.n + kPermPad && n_quad <= 2u * a.n, CK_LIST)) sid = kNoStream;
+    if (sid != kNoStream && !(ALACGPU_CHECK(a.check, sid < 2u * a.n, CK_LIST) &&
+                              ALACGPU_CHECK(a.check, ((uint64_t)sid + 1u) * a.ns * 4u <= a.plane_bytes, CK_PLANE)))
+        sid = kNoStream;
     const bool active = sid != kNoStream;
     int n = 0, rss = 32, ord = 0, q = 0;
     const int16_t *coef16 = nullptr;

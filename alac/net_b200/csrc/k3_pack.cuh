@@ -57,7 +57,7 @@ __device__ __forceinline__ void read_pairs(const uint32_t *__restrict__ arena32,
 __device__ __forceinline__ bool pack_group(const ChunkArgs &a, const uint32_t slot, const uint32_t i0,
                                            uint32_t (&w)[12], uint32_t &nbytes, uint32_t &cnt, uint8_t *&dst)
 {
-
+    if (!ALACGPU_CHECK(a.check, slot < a.n, CK_FRAME)) return false;
     const uint64_t f = a.f0 + slot;
     const FrameDesc d = a.desc[f];
     const FrameRef ref = a.refs[f];
@@ -81,6 +81,7 @@ __device__ __forceinline__ bool pack_group(const ChunkArgs &a, const uint32_t sl
 #pragma unroll
     for (int s = 0; s < 8; s++) { L[s] = 0; R[s] = 0; }
 
+    if (ok && !escape && !ALACGPU_CHECK(a.check, (((uint64_t)slot * 2u + 1u) * a.ns + i0 + 8u) * 4u <= a.plane_bytes, CK_PLANE)) return false;
     if (ok && !escape) {
         // predicted samples: rows are padded to a multiple of 8, so the loads never leave the row
         const int4 *ra = reinterpret_cast<const int4 *>(a.planes + ((uint64_t)slot * 2u) * a.ns + i0);
@@ -162,6 +163,9 @@ __device__ __forceinline__ bool pack_group(const ChunkArgs &a, const uint32_t sl
     }
     nbytes = cnt * bpf;                                               // 16, 24, 32 or 48 when cnt == 8
     dst = a.pcm + (a.frame_off[f] - a.pcm_base) + (uint64_t)i0 * bpf;
+    // (checked build) the group lies inside the PCM buffer
+    if (!ALACGPU_CHECK(a.check, a.frame_off[f] >= a.pcm_base && (a.frame_off[f] - a.pcm_base) + (uint64_t)i0 * bpf + nbytes <= a.pcm_bytes, CK_PCM))
+        return false;
     return true;
 }
 

@@ -34,6 +34,7 @@
 //
 // HBM traffic per 16-bit stereo sample-frame: compressed bytes once, 2 + 2 bytes of channel-A
 // plane, 4 bytes of PCM -- no clear, no residual plane, no second pass over the samples.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -73,8 +74,15 @@ __device__ __forceinline__ KfClass kf_classify(const FrameDesc &d, const TrackCf
 // (grid order of the classes, kf_scan: heaviest predictor first -- 30 .. 1 -- then delta mode, then order 0)
 
 // kf_count: [0] phase-A entries (padded), [1] phase-B entries (padded), [2] pack-only frames, then
-// hist[2][256] at 8 and cursor[2][256] at 8 + 512.
-constexpr uint32_t kHist = 8, kCursor = 8 + 2 * kKfClasses;
+// hist[2][256] at 8, cursor[2][256] behind it, and the per-SM schedule of the two phases (see kf_frames):
+// seg_bound[2][kMaxSeg + 1] (warp index where segment s of the class-sorted list starts), seg_next[2][kMaxSeg]
+// (warps handed out per segment), sm_seg[2][kMaxSm] (segment claimed by SM id: 0 none, 1 being claimed,
+// s + 2), seg_claim[2] (segments claimed so far).
+constexpr uint32_t kMaxSeg = 256, kMaxSm = 512;
+constexpr uint32_t kHist = 8, kCursor = kHist + 2 * kKfClasses;
+constexpr uint32_t kSegBound = kCursor + 2 * kKfClasses, kSegNext = kSegBound + 2 * (kMaxSeg + 1);
+constexpr uint32_t kSmSeg = kSegNext + 2 * kMaxSeg, kSegClaim = kSmSeg + 2 * kMaxSm;
+static_assert(kSegClaim + 2 <= kKfCountWords, "kf_count scratch too small");
 
 __global__ void __launch_bounds__(256)
 kf_hist(const FrameDesc *__restrict__ desc, const FrameRef *__restrict__ refs, const TrackCfg *__restrict__ cfgs,
@@ -95,21 +103,52 @@ kf_hist(const FrameDesc *__restrict__ desc, const FrameRef *__restrict__ refs, c
         if (h[k]) atomicAdd(&cnt[kHist + k], h[k]);
 }
 
-__global__ void __launch_bounds__(256)
-kf_scan(uint32_t *__restrict__ cnt, const uint32_t list_cap)
+// class r-th in grid order; instructions one warp issues per sample of that class (entropy step + taps + output)
+__device__ __forceinline__ uint32_t kf_class_at(uint32_t r)
 {
-    // class -> start of its (padded) range, in grid order; one thread per list
+    const uint32_t rr = r / 8u, kind = r % 8u;
+    const uint32_t order = rr == 31 ? 0u : (rr == 30 ? 31u : 30u - rr);
+    return kind * 32u + order;
+}
+__device__ __forceinline__ uint32_t kf_class_weight(uint32_t cls)
+{
+    const uint32_t order = cls & 31u;
+    return 170u + (order == 31u ? 10u : 10u * order);
+}
+
+__global__ void __launch_bounds__(256)
+kf_scan(uint32_t *__restrict__ cnt, const uint32_t list_cap, const uint32_t nseg)
+{
+    // one thread per list: class -> start of its (padded) range, in grid order; then the list is cut into
+    // `nseg` contiguous segments of equal estimated work, one per SM (kf_frames)
     if (threadIdx.x < 2) {
         const uint32_t l = threadIdx.x;
         uint32_t acc = 0;
+        unsigned long long work = 0;
         for (uint32_t r = 0; r < kKfClasses; r++) {
-            const uint32_t rr = r / 8u, kind = r % 8u;
-            const uint32_t order = rr == 31 ? 0u : (rr == 30 ? 31u : 30u - rr);
-            const uint32_t cls = kind * 32u + order;
+            const uint32_t cls = kf_class_at(r);
             cnt[kCursor + l * kKfClasses + cls] = l * list_cap + acc;
-            acc += (cnt[kHist + l * kKfClasses + cls] + 31u) & ~31u;
+            const uint32_t padded = (cnt[kHist + l * kKfClasses + cls] + 31u) & ~31u;
+            acc += padded;
+            work += (unsigned long long)(padded / 32u) * kf_class_weight(cls);
         }
         cnt[l] = acc;
+        uint32_t *bound = cnt + kSegBound + l * (kMaxSeg + 1);
+        uint32_t s = 1, warp0 = 0;
+        unsigned long long cum = 0;
+        bound[0] = 0;
+        for (uint32_t r = 0; r < kKfClasses && s < nseg; r++) {
+            const uint32_t cls = kf_class_at(r);
+            const uint32_t warps = ((cnt[kHist + l * kKfClasses + cls] + 31u) & ~31u) / 32u;
+            const unsigned long long w = kf_class_weight(cls);
+            while (s < nseg && work * s <= (cum + warps * w) * nseg) {      // target(s) = work * s / nseg falls inside this class
+                const unsigned long long target = work * s / nseg;
+                bound[s++] = warp0 + (uint32_t)((target > cum ? target - cum : 0ull) / w);
+            }
+            cum += warps * w;
+            warp0 += warps;
+        }
+        for (; s <= nseg; s++) bound[s] = acc / 32u;
     }
 }
 
@@ -163,9 +202,22 @@ struct OutStage {
     uint8_t *g;          // global address of position 0 (16-byte aligned)
     uint32_t s;          // shared-space address of the ring
     uint32_t p, F, head; // next byte position; flushed up to (multiple of 16); first own byte of group 0 (0 once it is out)
+#ifdef ALACGPU_CHECKED
+    uint64_t room;       // bytes from position 0 to the end of the destination buffer
+    uint32_t *chk;
+    int what;
+#endif
 
-    __device__ __forceinline__ void init(uint8_t *dst, uint32_t saddr)
+    __device__ __forceinline__ void init(uint8_t *dst, uint32_t saddr, const uint8_t *buf = nullptr, uint64_t buf_bytes = 0,
+                                         uint32_t *check = nullptr, int code = 0)
     {
+#ifdef ALACGPU_CHECKED
+        chk = check;
+        what = code;
+        const bool inside = ALACGPU_CHECK(chk, dst >= buf && dst <= buf + buf_bytes, code);
+        if (!inside) dst = const_cast<uint8_t *>(buf);
+        room = (uint64_t)(buf + buf_bytes - dst) + ((uintptr_t)dst & 15u);
+#endif
         head = (uint32_t)((uintptr_t)dst & 15u);
         g = dst - head;
         s = saddr;
@@ -201,9 +253,15 @@ struct OutStage {
             F = 16u;
         }
         const uint32_t go = head == 0u ? 1u : 0u;
+#ifdef ALACGPU_CHECKED
+        ALACGPU_CHECK(chk, p - F <= kStageRing + 15u, CK_RING);      // nothing was overwritten before it left
+#endif
 #pragma unroll
         for (int k = 0; k < kGroups; k++) {
-            const uint32_t on = (go != 0u && F + 16u <= p) ? 1u : 0u;
+            uint32_t on = (go != 0u && F + 16u <= p) ? 1u : 0u;
+#ifdef ALACGPU_CHECKED
+            if (on && !ALACGPU_CHECK(chk, (uint64_t)F + 16u <= room, what)) on = 0u;
+#endif
             uint4 v;
             asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %6, 0;\n\t"
                          "@q ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t"
@@ -216,6 +274,9 @@ struct OutStage {
     __device__ __forceinline__ void finish()       // the last, partial group (and group 0 of a very short frame)
     {
         const uint32_t lo = max(F, head);
+#ifdef ALACGPU_CHECKED
+        if (lo < p && !ALACGPU_CHECK(chk, (uint64_t)p <= room, what)) { F = p; return; }
+#endif
         if (lo < p) stage_bytes(g, s, lo, p);
         F = p;
     }
@@ -435,13 +496,16 @@ template <int M, bool kB>
 __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, const bool valid, uint8_t *wsm)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t slot = valid ? slot_in : 0u;
+    const bool in_chunk = ALACGPU_CHECK(a.check, !valid || slot_in < a.n, CK_FRAME);
+    const uint32_t slot = (valid && in_chunk) ? slot_in : 0u;
     const uint64_t f = a.f0 + slot;
     const FrameDesc d = a.desc[f];
     const FrameRef ref = a.refs[f];
     const TrackCfg cfg = a.cfgs[ref.track];
     constexpr int ch = kB ? 1 : 0;
-    const bool work = valid && d.status == FS_OK;                   // phase B: channel A may have failed in phase A
+    bool work = valid && in_chunk && d.status == FS_OK;             // phase B: channel A may have failed in phase A
+    // (checked build) the frame's channel-A row lies inside the slot's plane
+    if (work && !ALACGPU_CHECK(a.check, ((uint64_t)slot + 1u) * a.ns * 4u <= a.plane_bytes && d.n <= a.ns, CK_PLANE)) work = false;
     const uint32_t n = work ? (uint32_t)d.n : 0u;
     const bool is24 = cfg.sample_size == 24;
     const bool stereo = (d.flags & FF_STEREO) != 0;
@@ -460,7 +524,7 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
     const uint32_t kk0 = min(exp_of(0x4B000000u | (uint32_t)((h0 >> 9) + 3)), kcap);
     const uint32_t start_bit = kB ? a.bstart[slot] : d.data_bit;
     BitCursor br;
-    br.init(a.arena, work ? ref.off * 8ull + start_bit : 0ull, wsm + (uint32_t)lane * (uint32_t)kRingBytes);
+    br.init(a.arena, work ? ref.off * 8ull + start_bit : 0ull, wsm + (uint32_t)lane * (uint32_t)kRingBytes, a.arena_bytes, a.check);
     const uint32_t mult = (uint32_t)((int32_t)d.rice_mod[ch] * (cfg.rice_history_mult / 4));
     uint32_t i = 0, nc = n;
     int32_t h = h0;
@@ -477,7 +541,9 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
     OutStage out;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(wsm + kRingBytes * 32u) + (uint32_t)lane * kStageStride;
     const bool to_plane = !kB && stereo_w;
-    out.init(to_plane ? plane_row : a.pcm + (a.frame_off[f] - a.pcm_base), stage_addr);
+    out.init(to_plane ? plane_row : a.pcm + (a.frame_off[f] - a.pcm_base), stage_addr,
+             to_plane ? reinterpret_cast<const uint8_t *>(a.planes) : a.pcm, to_plane ? a.plane_bytes : a.pcm_bytes, a.check,
+             to_plane ? CK_PLANE : CK_PCM);
     PlaneRing ar;
     if (kB) {
         ar.init(plane_row, (uint32_t)__cvta_generic_to_shared(wsm + kKfWarpSmemA) + (uint32_t)lane * kARingStride,
@@ -581,30 +647,72 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
     }
 }
 
+// Persistent warps with a per-SM schedule.  The loop of one class is 5-10 KB of code (the taps are unrolled:
+// coefficients and history live in registers), an SM's instruction cache holds 32 KB (6 KB per sub-partition),
+// and a plain grid hands consecutive blocks to DIFFERENT SMs -- so every SM would run eight classes at once
+// and fetch its instructions from L2 (measured: 65 % of all issue slots lost to instruction-fetch stalls, every
+// one on the first instruction of a 128-byte line).  Instead the class-sorted list is cut into one segment of
+// equal estimated work per SM; the warps of an SM claim one segment and walk it front to back, so the whole
+// SM executes one class (two at a boundary) at a time.  A warp that finds its segment empty moves on to the
+// next segment that still has work (and stays there), which evens out the tail.  Nothing ever waits on
+// another warp: the schedule is only a matter of who takes which 32 frames.
 template <bool kB>
 __global__ void __launch_bounds__(kKfThreads, kB ? 5 : 8)
-kf_frames(const ChunkArgs a)
+kf_frames(const ChunkArgs a, const uint32_t nseg)
 {
     extern __shared__ __align__(256) uint8_t smem[];
-    const uint32_t idx = blockIdx.x * kKfThreads + threadIdx.x;
-    const uint32_t total = a.kf_count[kB ? 1 : 0];
-    if ((idx & ~31u) >= total) return;                                      // the whole warp is past the list
-    const uint32_t slot = a.kf_list[(kB ? a.kf_cap : 0u) + idx];
-    const bool valid = slot != kNoSlot;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t l = kB ? 1u : 0u;
+    uint32_t *const cnt = a.kf_count;
+    const uint32_t *const bound = cnt + kSegBound + l * (kMaxSeg + 1);
+    uint32_t *const next = cnt + kSegNext + l * kMaxSeg;
     uint8_t *wsm = smem + (threadIdx.x >> 5) * (kB ? kKfWarpSmemB : kKfWarpSmemA);
-    int order = 0;
-    if (valid) order = a.desc[a.f0 + slot].order[kB ? 1 : 0];
-    const int M = __shfl_sync(0xffffffffu, order, 0);                      // the warp's class (lane 0 is never padding)
-#define ALACGPU_KF(MM) case MM: kf_run<MM, kB>(a, slot, valid, wsm); break
-    switch (M) {
-        ALACGPU_KF(0); ALACGPU_KF(1); ALACGPU_KF(2); ALACGPU_KF(3); ALACGPU_KF(4); ALACGPU_KF(5); ALACGPU_KF(6);
-        ALACGPU_KF(7); ALACGPU_KF(8); ALACGPU_KF(9); ALACGPU_KF(10); ALACGPU_KF(11); ALACGPU_KF(12); ALACGPU_KF(13);
-        ALACGPU_KF(14); ALACGPU_KF(15); ALACGPU_KF(16); ALACGPU_KF(17); ALACGPU_KF(18); ALACGPU_KF(19); ALACGPU_KF(20);
-        ALACGPU_KF(21); ALACGPU_KF(22); ALACGPU_KF(23); ALACGPU_KF(24); ALACGPU_KF(25); ALACGPU_KF(26); ALACGPU_KF(27);
-        ALACGPU_KF(28); ALACGPU_KF(29); ALACGPU_KF(30); ALACGPU_KF(31);
-        default: break;
+    uint32_t seg = 0;
+    if (lane == 0) {                                      // the segment of this SM: the first warp to arrive claims one
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        uint32_t *slot = cnt + kSmSeg + l * kMaxSm + (smid & (kMaxSm - 1u));
+        uint32_t v = atomicCAS(slot, 0u, 1u);
+        if (v == 0u) {
+            v = atomicAdd(cnt + kSegClaim + l, 1u) % nseg + 2u;
+            atomicExch(slot, v);
+        } else {
+            while (v < 2u) v = *reinterpret_cast<volatile uint32_t *>(slot);     // the claimer is a few instructions away
+        }
+        seg = v - 2u;
     }
+    for (;;) {
+        uint32_t w = kNoSlot;                              // next warp-sized piece of the list
+        if (lane == 0) {
+            for (uint32_t k = 0; k < nseg; k++) {
+                uint32_t s2 = seg + k;
+                if (s2 >= nseg) s2 -= nseg;
+                const uint32_t lo = bound[s2], n_here = bound[s2 + 1] - lo;
+                if (*reinterpret_cast<volatile uint32_t *>(next + s2) >= n_here) continue;
+                const uint32_t it = atomicAdd(next + s2, 1u);
+                if (it < n_here) { w = lo + it; seg = s2; break; }
+            }
+        }
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w == kNoSlot) break;
+        uint32_t slot = kNoSlot;
+        if (ALACGPU_CHECK(a.check, w * 32u + 32u <= a.kf_cap, CK_LIST)) slot = a.kf_list[(kB ? a.kf_cap : 0u) + w * 32u + (uint32_t)lane];
+        const bool valid = slot != kNoSlot;
+        int order = 0;
+        if (valid) order = a.desc[a.f0 + slot].order[kB ? 1 : 0];
+        const int M = __shfl_sync(0xffffffffu, order, 0);                  // the warp's class (lane 0 is never padding)
+#define ALACGPU_KF(MM) case MM: kf_run<MM, kB>(a, slot, valid, wsm); break
+        switch (M) {
+            ALACGPU_KF(0); ALACGPU_KF(1); ALACGPU_KF(2); ALACGPU_KF(3); ALACGPU_KF(4); ALACGPU_KF(5); ALACGPU_KF(6);
+            ALACGPU_KF(7); ALACGPU_KF(8); ALACGPU_KF(9); ALACGPU_KF(10); ALACGPU_KF(11); ALACGPU_KF(12); ALACGPU_KF(13);
+            ALACGPU_KF(14); ALACGPU_KF(15); ALACGPU_KF(16); ALACGPU_KF(17); ALACGPU_KF(18); ALACGPU_KF(19); ALACGPU_KF(20);
+            ALACGPU_KF(21); ALACGPU_KF(22); ALACGPU_KF(23); ALACGPU_KF(24); ALACGPU_KF(25); ALACGPU_KF(26); ALACGPU_KF(27);
+            ALACGPU_KF(28); ALACGPU_KF(29); ALACGPU_KF(30); ALACGPU_KF(31);
+            default: break;
+        }
 #undef ALACGPU_KF
+        __syncwarp();
+    }
 }
 
 // ---- pack-only frames (uncompressed, or failed at the header): k3's code over the work list --------
@@ -647,6 +755,17 @@ kf_fix_failed(const ChunkArgs a)
     }
 }
 
+// one segment of the class-sorted list per SM of the current device
+static uint32_t kf_segments()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); sms = 148; }
+    static const int env = getenv("ALACGPU_KF_SEGMENTS") ? atoi(getenv("ALACGPU_KF_SEGMENTS")) : 0;
+    if (env > 0) sms = env;
+    return (uint32_t)std::min<int>(std::max(sms, 1), (int)kMaxSeg);
+}
+
 // (attributes are per device: set on the current one every time, a cheap driver call)
 cudaError_t launch_kf_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
@@ -655,18 +774,42 @@ cudaError_t launch_kf_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launch
     if (cudaError_t e = cudaMemsetAsync(a.kf_list, 0xFF, 2u * (size_t)a.kf_cap * sizeof(uint32_t), st)) return e;
     const uint32_t nb = (a.n + 255u) / 256u;
     kf_hist<<<nb, 256, 0, st>>>(a.desc + a.f0, a.refs + a.f0, a.cfgs, a.n, a.kf_count);
-    kf_scan<<<1, 256, 0, st>>>(a.kf_count, a.kf_cap);
+    kf_scan<<<1, 256, 0, st>>>(a.kf_count, a.kf_cap, kf_segments());
     kf_scatter<<<nb, 256, 0, st>>>(a.desc + a.f0, a.refs + a.f0, a.cfgs, a.n, a.kf_count, a.kf_list, a.kf_cap);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }
 
+// The frame-lane kernels live on shared memory (three lane-private rings per lane) and barely use L1: ask for
+// the largest shared-memory carve-out so that the register file, not the carve-out, bounds the blocks per SM.
+template <bool kB>
+static cudaError_t kf_attributes(int *blocks_per_sm)
+{
+    const int smem = 2 * (int)(kB ? kKfWarpSmemB : kKfWarpSmemA);
+    if (cudaError_t e = cudaFuncSetAttribute(kf_frames<kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) return e;
+    if (cudaError_t e = cudaFuncSetAttribute(kf_frames<kB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return e;
+    int nb = 0;
+    if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf_frames<kB>, kKfThreads, smem)) return e;
+    *blocks_per_sm = std::max(nb, 1);
+    static const bool dbg = getenv("ALACGPU_DEBUG_OCC") != nullptr;
+    if (dbg) {
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, kf_frames<kB>);
+        fprintf(stderr, "[alacgpu] kf_frames<%c>: %d blocks/SM of %d threads, %d registers, %d B dynamic smem, %zu B local\n",
+                kB ? 'B' : 'A', nb, kKfThreads, fa.numRegs, smem, fa.localSizeBytes);
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    if (cudaError_t e = cudaFuncSetAttribute(kf_frames<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKfWarpSmemA)) return e;
-    const uint32_t blocks = a.kf_cap / kKfThreads;           // upper bound; warps past the list exit at once
-    kf_frames<false><<<blocks, kKfThreads, 2 * kKfWarpSmemA, st>>>(a);
+    int per_sm = 1;
+    if (cudaError_t e = kf_attributes<false>(&per_sm)) return e;
+    const uint32_t nseg = kf_segments();
+    // persistent warps: as many blocks as fit the machine at once (fewer for a chunk that cannot fill it)
+    const uint32_t blocks = std::min<uint32_t>(nseg * (uint32_t)per_sm, a.kf_cap / kKfThreads);
+    kf_frames<false><<<blocks, kKfThreads, 2 * kKfWarpSmemA, st>>>(a, nseg);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -674,9 +817,11 @@ cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 cudaError_t launch_kf_b(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    if (cudaError_t e = cudaFuncSetAttribute(kf_frames<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKfWarpSmemB)) return e;
-    const uint32_t blocks = a.kf_cap / kKfThreads;
-    kf_frames<true><<<blocks, kKfThreads, 2 * kKfWarpSmemB, st>>>(a);
+    int per_sm = 1;
+    if (cudaError_t e = kf_attributes<true>(&per_sm)) return e;
+    const uint32_t nseg = kf_segments();
+    const uint32_t blocks = std::min<uint32_t>(nseg * (uint32_t)per_sm, a.kf_cap / kKfThreads);
+    kf_frames<true><<<blocks, kKfThreads, 2 * kKfWarpSmemB, st>>>(a, nseg);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -27,11 +27,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "alacgpu_device.cuh"
 #include "alacgpu_kernels.h"
+#include "host_staging.h"
 
 using namespace alacgpu;
 
@@ -51,6 +56,7 @@ constexpr uint64_t kFrameLaneMinFrames = 65536;
 constexpr uint32_t kFrameLaneMaxChunk = 262144;
 constexpr uint64_t kFrameLanePlaneBudget = 16ull << 30;   // bytes of channel-A planes over all slots in flight
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
+constexpr uint64_t kRingSlotBytes = 16ull << 20;   // one slot of the page-locked staging rings (host_staging.h)
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -102,7 +108,7 @@ struct HostTrack {
     std::vector<uint64_t> offs;   // explicit byte offset of every frame (empty: frames are back to back)
 };
 
-struct HostCopy { const uint8_t *src; uint64_t dst, len; };
+struct HostCopy { const uint8_t *src; uint64_t dst, len; bool pinned; };   // pinned: the caller's memory is page-locked
 
 struct Chunk {
     uint64_t f0;                  // device-local first frame
@@ -146,6 +152,8 @@ struct Device {
     std::vector<Chunk> chunks;
     uint32_t chunk_frames = 0;
     bool chunk_taper = false;
+    PinnedRing ring_in, ring_out;     // page-locked staging for pageable callers (host_staging.h)
+    std::unique_ptr<Progress> h2d_prog, k_prog;   // stager -> issuer -> drainer hand-over of recorded events
     bool frame_lanes = false;         // this pipeline run decodes with the frame-lane kernels
     int slots_n = kSlots;             // slot streams in use by this pipeline run
     std::vector<cudaEvent_t> events;
@@ -163,6 +171,8 @@ struct alacgpu_ctx {
     std::vector<uint32_t> out_len;        // PCM bytes of every frame (host rule == K0 rule)
     std::vector<uint64_t> frame_off;      // global padded PCM offset of every frame
     alacgpu_opts opts{};
+    std::unique_ptr<CopyPool> pool;       // host threads that move bytes between caller memory and the staging rings
+    std::mutex pool_mutex;
     bool planned = false;
     uint64_t total_pcm = 0;
     uint64_t compressed_bytes = 0;
@@ -266,6 +276,15 @@ void invalidate(alacgpu_ctx *ctx)
     for (Device &d : ctx->devs) { d.resident = false; d.decoded = false; d.pcm_resident = false; d.chunk_frames = 0; d.chunks.clear(); }
 }
 
+// Is `p` page-locked (cudaHostAlloc / cudaHostRegister / alacgpu_host_alloc) memory?
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) return true;
+    cudaGetLastError();
+    return false;
+}
+
 // Partition + per-device frame index.  Pure host work plus allocations and the small table
 // uploads (on the H2D stream, ahead of any mdat copy).
 int32_t build_plan(alacgpu_ctx *ctx)
@@ -332,7 +351,7 @@ int32_t build_plan(alacgpu_ctx *ctx)
                 d.h_refs[f - d.f_lo] = r;
                 compressed += r.len;
             }
-            if (src_hi > src_lo && !ht.staged) d.track_copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo});
+            if (src_hi > src_lo && !ht.staged) d.track_copies.push_back({ht.mdat + src_lo, base, src_hi - src_lo, is_pinned(ht.mdat)});
             used = base + (src_hi - src_lo);
         }
         d.arena_used = used;
@@ -416,7 +435,7 @@ void build_chunks(alacgpu_ctx *ctx, Device &d, uint32_t cf, bool taper)
             if (hi > lo)
                 for (const HostCopy &hc : d.track_copies)       // one staged range per (track, device)
                     if (lo >= hc.dst && lo < hc.dst + hc.len) {
-                        d.copies.push_back({hc.src + (lo - hc.dst), lo, std::min(hi, hc.dst + hc.len) - lo});
+                        d.copies.push_back({hc.src + (lo - hc.dst), lo, std::min(hi, hc.dst + hc.len) - lo, hc.pinned});
                         break;
                     }
             f = e;
@@ -433,8 +452,18 @@ constexpr size_t kEvPerChunk = 6;   // start, after K0, K1, K2, K3, h2d-done
 constexpr size_t kEvBase = 4;       // [0] pipeline start, [1] pipeline end, [2] d2h start, [3] d2h end
 
 // Issue one chunk's kernels on its slot stream.
+// (errors go to *err, not to ctx->err: several devices issue from their own threads)
+#define CUI(call)                                                                                \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            if (err) { *err = #call; *err += ": "; *err += cudaGetErrorString(e_); }             \
+            return e_ == cudaErrorMemoryAllocation ? ALACGPU_ERR_OUT_OF_MEMORY : ALACGPU_ERR_CUDA; \
+        }                                                                                        \
+    } while (0)
+
 int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool with_k0, bool with_decode,
-                    size_t ev, uint32_t *launches, uint8_t *pcm_override, bool streaming, bool early = false)
+                    size_t ev, uint32_t *launches, uint8_t *pcm_override, bool streaming, bool early, std::string *err)
 {
     ChunkArgs ca{};
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
@@ -467,15 +496,15 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
         ca.kf_count = s.kf.p + kf_list_words(d.chunk_frames);
         ca.bstart = ca.kf_count + kKfCountWords;
     }
-    CU(cudaEventRecord(get_event(d, ev), s.st));
+    CUI(cudaEventRecord(get_event(d, ev), s.st));
     if (with_k0) {
         K0Args ka{};
         ka.arena = d.arena.p; ka.refs = d.refs.p; ka.cfgs = d.cfgs.p; ka.desc = d.desc.p; ka.coefs = d.coefs.p;
         ka.expect_len = d.expect_len.p; ka.mismatch = reinterpret_cast<uint32_t *>(d.scalars.p);
         ka.f0 = c.f0; ka.n = c.n;
-        CU(launch_k0(ka, s.st, launches));
+        CUI(launch_k0(ka, s.st, launches));
     }
-    CU(cudaEventRecord(get_event(d, ev + 1), s.st));
+    CUI(cudaEventRecord(get_event(d, ev + 1), s.st));
     // fusion level: 2 = entropy + LPC + pack in one launch, 1 = entropy + LPC with K3 apart, 0 = three
     // kernels.  Measured on configs[1] (one B200): level 1 is the fastest way to PCM in HBM (3.54 ms;
     // the pack blocks of level 2 only get SM slots once producers retire: 4.23 ms) and while chunks are
@@ -487,34 +516,32 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     if (pcm_override) { ca.pcm = pcm_override; ca.pcm_base = 0; }      // PCM straight into host-mapped memory
     if (d.frame_lanes) {
         // frame-lane kernels: sort + phase A | phase B | pack-only frames + fix-up (timing slots: entropy, lpc, stereo)
-        if (with_decode) { CU(launch_kf_sort(ca, s.st, launches)); CU(launch_kf_a(ca, s.st, launches)); }
-        CU(cudaEventRecord(get_event(d, ev + 2), s.st));
-        if (with_decode) CU(launch_kf_b(ca, s.st, launches));
-        CU(cudaEventRecord(get_event(d, ev + 3), s.st));
-        if (with_decode) CU(launch_kf_rest(ca, s.st, launches));
-        CU(cudaEventRecord(get_event(d, ev + 4), s.st));
+        if (with_decode) { CUI(launch_kf_sort(ca, s.st, launches)); CUI(launch_kf_a(ca, s.st, launches)); }
+        CUI(cudaEventRecord(get_event(d, ev + 2), s.st));
+        if (with_decode) CUI(launch_kf_b(ca, s.st, launches));
+        CUI(cudaEventRecord(get_event(d, ev + 3), s.st));
+        if (with_decode) CUI(launch_kf_rest(ca, s.st, launches));
+        CUI(cudaEventRecord(get_event(d, ev + 4), s.st));
         return ALACGPU_OK;
     }
     if (with_decode) {
-        CU(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
-        if (fused) CU(cudaMemsetAsync(s.progress.p, 0, (2u * cf2 + 4u) * sizeof(uint32_t), s.st));
-        if (fused == 2) CU(launch_k123(ca, lanes_for(ctx), s.st, launches));
-        else if (fused == 1) CU(launch_k12(ca, lanes_for(ctx), s.st, launches));
-        else CU(launch_k1(ca, lanes_for(ctx), s.st, launches));
+        CUI(launch_sort(ca, s.st, launches));             // after K0: the work list needs only the headers
+        if (fused) CUI(cudaMemsetAsync(s.progress.p, 0, (2u * cf2 + 4u) * sizeof(uint32_t), s.st));
+        if (fused == 2) CUI(launch_k123(ca, lanes_for(ctx), s.st, launches));
+        else if (fused == 1) CUI(launch_k12(ca, lanes_for(ctx), s.st, launches));
+        else CUI(launch_k1(ca, lanes_for(ctx), s.st, launches));
     }
-    CU(cudaEventRecord(get_event(d, ev + 2), s.st));
-    if (with_decode && fused == 0) CU(launch_k2(ca, s.st, launches));
-    CU(cudaEventRecord(get_event(d, ev + 3), s.st));
+    CUI(cudaEventRecord(get_event(d, ev + 2), s.st));
+    if (with_decode && fused == 0) CUI(launch_k2(ca, s.st, launches));
+    CUI(cudaEventRecord(get_event(d, ev + 3), s.st));
     if (with_decode) {
-        if (fused == 2) CU(launch_fix(ca, s.st, launches));
-        else CU(launch_k3(ca, s.st, launches));
+        if (fused == 2) CUI(launch_fix(ca, s.st, launches));
+        else CUI(launch_k3(ca, s.st, launches));
     }
-    CU(cudaEventRecord(get_event(d, ev + 4), s.st));
+    CUI(cudaEventRecord(get_event(d, ev + 4), s.st));
     return ALACGPU_OK;
 }
 
-// The whole pipeline on every device.  stage: copy mdat to the arena (chunk by chunk);
-// index: run K0; decode: run K1-K3; pcm_dst: copy PCM back chunk by chunk.
 // Stage timings of the last pipeline, from the CUDA events its streams recorded (max over devices).
 void finish_timing(alacgpu_ctx *ctx)
 {
@@ -566,45 +593,293 @@ void finish_timing(alacgpu_ctx *ctx)
     if (ctx->tp_d2h) tm.d2h_ms = to_host ? d2h : 0.f;
 }
 
+struct PipeArgs {
+    bool stage, index, decode;
+    uint8_t *pcm_dst;       // caller's host buffer (or null)
+    uint8_t *zc;            // device alias of pcm_dst when the pack roles write into it directly
+    bool dst_pinned;
+    uint32_t cf_override;   // 0 = automatic
+};
+
+struct DevRun {             // what one device's pipeline run reports back
+    int32_t rc = ALACGPU_OK;
+    std::string err;
+    uint32_t launches = 0, chunks = 0, faults = 0;
+    std::mutex m;
+    void set_error(int32_t code, const char *what, cudaError_t e)
+    {
+        std::lock_guard<std::mutex> g(m);
+        if (rc != ALACGPU_OK) return;
+        rc = code;
+        err = what;
+        if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
+    }
+};
+
+// CUDA call inside a per-device worker: record the first error and leave
+#define CUD(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            res.set_error(e_ == cudaErrorMemoryAllocation ? ALACGPU_ERR_OUT_OF_MEMORY : ALACGPU_ERR_CUDA, #call, e_); \
+            return false;                                                                                \
+        }                                                                                                \
+    } while (0)
+
+uint64_t frame_lane_min_frames()
+{
+    static const uint64_t v = getenv("ALACGPU_KF_MIN") ? strtoull(getenv("ALACGPU_KF_MIN"), nullptr, 10) : kFrameLaneMinFrames;
+    return v;
+}
+
+bool frame_lanes_for(const alacgpu_ctx *ctx, const Device &d)
+{
+    if (ctx->opts.flags & (ALACGPU_FLAG_NO_FRAME_LANES | ALACGPU_FLAG_NO_FUSION)) return false;
+    if (ctx->opts.flags & ALACGPU_FLAG_FORCE_FRAME_LANES) return true;
+    return d.f_hi - d.f_lo >= frame_lane_min_frames();
+}
+
+// chunk size: as much as possible in flight at once when the bytes are already resident; ~kSlots chunks when
+// streaming from the host so copies and kernels overlap
+uint32_t chunk_frames_for(const alacgpu_ctx *ctx, const Device &d, bool stage)
+{
+    const uint64_t n_local = d.f_hi - d.f_lo;
+    const bool kf = frame_lanes_for(ctx, d);
+    const uint32_t cap = kf ? kFrameLaneMaxChunk : kMaxChunkFrames;
+    uint32_t cf = ctx->opts.chunk_frames;
+    if (!cf) {
+        if (stage) cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
+        else cf = (uint32_t)std::min<uint64_t>(n_local, cap);
+    }
+    return std::min<uint32_t>((cf + 31u) & ~31u, cap);
+}
+
+// One device's share of a pipeline run: issue every chunk (H2D of its mdat -> kernels -> D2H of its PCM) and
+// wait for it.  Runs on the caller's thread for a single-device context and on one thread per device
+// otherwise.  When the caller's memory is pageable, two helper threads keep the three stages independent:
+//   stager : caller bytes -> page-locked ring (copy pool) -> HBM, records "chunk c is on its way" events
+//   issuer : (this thread) kernels of chunk c once the stager has recorded c's event
+//   drainer: HBM -> page-locked ring -> caller's buffer (copy pool), chunk by chunk behind the kernels
+bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
+{
+    const uint64_t n_local = d.f_hi - d.f_lo;
+    if (!n_local) return true;
+    CUD(cudaSetDevice(d.id));
+    const bool stage = pa.stage, index = pa.index, decode = pa.decode;
+    uint8_t *const pcm_dst = pa.pcm_dst;
+    uint8_t *const zc = pa.zc;
+    const uint32_t cf = chunk_frames_for(ctx, d, stage);
+    d.frame_lanes = frame_lanes_for(ctx, d);
+    static const bool no_taper = getenv("ALACGPU_NO_TAPER") != nullptr;
+    build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper && !d.frame_lanes);
+    const size_t n_chunks = d.chunks.size();
+    // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
+    d.slots_n = kSlots;
+    if (d.frame_lanes)
+        d.slots_n = (int)std::max<uint64_t>(3, std::min<uint64_t>(kSlots, kFrameLanePlaneBudget / ((uint64_t)cf * d.ns * 4u)));
+    const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
+    if (decode)
+        for (int s = 0; s < slots_used; s++) {
+            if (d.frame_lanes) {
+                CUD(d.slots[s].planes.reserve((size_t)cf * d.ns + 64u));          // one row per frame (channel A)
+                CUD(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
+            } else {
+                CUD(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
+                CUD(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
+                CUD(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
+            }
+        }
+    const bool to_host = pcm_dst && !zc && decode;
+    bool ring_in = false;
+    if (stage)
+        for (const HostCopy &hc : d.copies) ring_in = ring_in || !hc.pinned;
+    const bool ring_out = to_host && !pa.dst_pinned;
+    static const bool no_ring = getenv("ALACGPU_NO_STAGING_RING") != nullptr;   // A/B: plain cudaMemcpyAsync on pageable memory
+    if (no_ring) ring_in = false;
+    const bool threaded = ring_in || (ring_out && !no_ring);
+    if (threaded) {
+        if (!ctx->pool) {
+            const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+            static const int env_threads = getenv("ALACGPU_COPY_THREADS") ? atoi(getenv("ALACGPU_COPY_THREADS")) : 0;
+            std::lock_guard<std::mutex> g(ctx->pool_mutex);
+            if (!ctx->pool) ctx->pool.reset(new CopyPool(env_threads > 0 ? env_threads : (int)std::min(12u, std::max(2u, hw / 2))));
+        }
+        if (ring_in) CUD(d.ring_in.ensure(kRingSlotBytes));
+        if (ring_out) CUD(d.ring_out.ensure(kRingSlotBytes));
+    }
+    get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
+    CUD(cudaEventRecord(d.events[0], d.slots[0].st));
+    for (int s = 1; s < slots_used; s++) CUD(cudaStreamWaitEvent(d.slots[s].st, d.events[0], 0));
+    if (to_host) {
+        CUD(cudaStreamWaitEvent(d.st_d2h, d.events[0], 0));
+        CUD(cudaEventRecord(d.events[2], d.st_d2h));
+    }
+
+    // ---- the three stages of one chunk ------------------------------------------------------------
+    auto stage_chunk = [&](size_t ci) -> bool {          // H2D of the chunk's mdat bytes, then its "bytes are coming" event
+        const Chunk &c = d.chunks[ci];
+        for (uint32_t k = c.copy_lo; k < c.copy_hi; k++) {
+            const HostCopy &hc = d.copies[k];
+            if (hc.pinned || !ring_in) {
+                CUD(cudaMemcpyAsync(d.arena.p + hc.dst, hc.src, hc.len, cudaMemcpyHostToDevice, d.st_h2d));
+                continue;
+            }
+            PinnedRing &r = d.ring_in;
+            for (uint64_t off = 0; off < hc.len; off += r.slot_bytes) {
+                const uint64_t n = std::min<uint64_t>(r.slot_bytes, hc.len - off);
+                const int j = r.next;
+                if (r.busy[j]) CUD(cudaEventSynchronize(r.ev[j]));
+                ctx->pool->copy(r.buf[j], hc.src + off, n);
+                CUD(cudaMemcpyAsync(d.arena.p + hc.dst + off, r.buf[j], n, cudaMemcpyHostToDevice, d.st_h2d));
+                CUD(cudaEventRecord(r.ev[j], d.st_h2d));
+                r.busy[j] = true;
+                r.next = (j + 1) % PinnedRing::kSlots;
+            }
+        }
+        CUD(cudaEventRecord(d.events[kEvBase + ci * kEvPerChunk + 5], d.st_h2d));
+        return true;
+    };
+    auto launch_chunk = [&](size_t ci) -> bool {         // the chunk's kernels on its slot stream
+        const Chunk &c = d.chunks[ci];
+        Slot &s = d.slots[ci % (size_t)d.slots_n];
+        const size_t ev = kEvBase + ci * kEvPerChunk;
+        if (stage) CUD(cudaStreamWaitEvent(s.st, d.events[ev + 5], 0));
+        std::string err;
+        uint32_t l = 0;
+        const int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &l, zc, stage, stage && ci < 3, &err);
+        res.launches += l;
+        res.chunks++;
+        if (r) { res.set_error(r, err.c_str(), cudaSuccess); return false; }
+        return true;
+    };
+    struct Flying { int slot; uint8_t *dst; uint64_t len; };
+    std::deque<Flying> flying;                            // D2H pieces in the ring, oldest first
+    auto land_one = [&]() -> bool {                       // oldest piece: wait for its DMA, copy it out to the caller
+        const Flying f = flying.front();
+        flying.pop_front();
+        CUD(cudaEventSynchronize(d.ring_out.ev[f.slot]));
+        ctx->pool->copy(f.dst, d.ring_out.buf[f.slot], f.len);
+        d.ring_out.busy[f.slot] = false;
+        return true;
+    };
+    auto drain_chunk = [&](size_t ci) -> bool {           // D2H of the chunk's PCM behind its last kernel
+        const Chunk &c = d.chunks[ci];
+        if (!(to_host && c.pcm_hi > c.pcm_lo)) return true;
+        const size_t ev = kEvBase + ci * kEvPerChunk;
+        CUD(cudaStreamWaitEvent(d.st_d2h, d.events[ev + 4], 0));
+        if (!ring_out || no_ring) {
+            CUD(cudaMemcpyAsync(pcm_dst + c.pcm_lo, d.pcm.p + (c.pcm_lo - d.pcm_lo), c.pcm_hi - c.pcm_lo,
+                                cudaMemcpyDeviceToHost, d.st_d2h));
+            return true;
+        }
+        PinnedRing &r = d.ring_out;
+        for (uint64_t off = c.pcm_lo; off < c.pcm_hi; off += r.slot_bytes) {
+            const uint64_t n = std::min<uint64_t>(r.slot_bytes, c.pcm_hi - off);
+            const int j = r.next;
+            while (r.busy[j]) if (!land_one()) return false;
+            CUD(cudaMemcpyAsync(r.buf[j], d.pcm.p + (off - d.pcm_lo), n, cudaMemcpyDeviceToHost, d.st_d2h));
+            CUD(cudaEventRecord(r.ev[j], d.st_d2h));
+            r.busy[j] = true;
+            r.next = (j + 1) % PinnedRing::kSlots;
+            flying.push_back({j, pcm_dst + off, n});
+        }
+        return true;
+    };
+
+    bool ok = true;
+    if (!threaded) {
+        for (size_t ci = 0; ci < n_chunks && ok; ci++) {
+            if (stage) ok = stage_chunk(ci);
+            ok = ok && launch_chunk(ci);
+            ok = ok && drain_chunk(ci);
+        }
+    } else {
+        d.h2d_prog->reset();
+        d.k_prog->reset();
+        std::thread stager, drainer;
+        if (stage)
+            stager = std::thread([&] {
+                if (cudaSetDevice(d.id) != cudaSuccess) { d.h2d_prog->fail(); return; }
+                for (size_t ci = 0; ci < n_chunks; ci++) {
+                    if (!stage_chunk(ci)) { d.h2d_prog->fail(); return; }
+                    d.h2d_prog->set(ci + 1);
+                }
+            });
+        if (to_host)
+            drainer = std::thread([&] {
+                bool good = cudaSetDevice(d.id) == cudaSuccess;
+                for (size_t ci = 0; ci < n_chunks && good; ci++) {
+                    if (!d.k_prog->wait_above(ci)) { good = false; break; }
+                    good = drain_chunk(ci);
+                }
+                while (good && !flying.empty()) good = land_one();
+                if (!good) res.set_error(ALACGPU_ERR_CUDA, "PCM drain failed", cudaSuccess);
+            });
+        for (size_t ci = 0; ci < n_chunks && ok; ci++) {
+            if (stage && !d.h2d_prog->wait_above(ci)) { ok = false; break; }
+            ok = launch_chunk(ci);
+            if (ok) d.k_prog->set(ci + 1);
+        }
+        if (!ok) d.k_prog->fail();
+        if (stager.joinable()) stager.join();
+        if (drainer.joinable()) drainer.join();
+        for (int j = 0; j < PinnedRing::kSlots; j++) d.ring_in.busy[j] = false;    // everything is waited for below
+        ok = ok && res.rc == ALACGPU_OK;
+    }
+    if (!ok) {
+        cudaDeviceSynchronize();
+        if (res.rc == ALACGPU_OK) res.set_error(ALACGPU_ERR_CUDA, "pipeline issue failed", cudaSuccess);
+        return false;
+    }
+    // join: slot 0 waits for the last chunk of every other slot, then stamps the end
+    for (size_t ci = n_chunks > (size_t)d.slots_n ? n_chunks - (size_t)d.slots_n : 0; ci < n_chunks; ci++)
+        if (ci % (size_t)d.slots_n != 0) CUD(cudaStreamWaitEvent(d.slots[0].st, d.events[kEvBase + ci * kEvPerChunk + 4], 0));
+    CUD(cudaEventRecord(d.events[1], d.slots[0].st));
+    if (to_host) CUD(cudaEventRecord(d.events[3], d.st_d2h));
+    // ---- wait ---------------------------------------------------------------------------------------
+    CUD(cudaStreamSynchronize(d.slots[0].st));
+    if (to_host) CUD(cudaStreamSynchronize(d.st_d2h));
+    if (stage) CUD(cudaStreamSynchronize(d.st_h2d));
+    if (stage || index) d.resident = true;
+    if (stage) d.arena_staged = d.arena_used;
+    if (decode) { d.decoded = true; d.pcm_resident = !zc; }     // zero-copy output leaves no PCM in HBM
+    if (index || decode) {
+        uint32_t sc[2] = {0, 0};                                   // [0] K0 size mismatches, [1] FS_INTERNAL frames
+        CUD(cudaMemcpy(sc, d.scalars.p, sizeof sc, cudaMemcpyDeviceToHost));
+        if (sc[0]) { res.set_error(ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size", cudaSuccess); return false; }
+        if (sc[1]) {
+            res.faults = sc[1];
+            CUD(cudaMemset(reinterpret_cast<uint32_t *>(d.scalars.p) + 1, 0, sizeof(uint32_t)));
+        }
+    }
+    return true;
+}
+
+// The whole pipeline on every device.  stage: copy mdat to the arena (chunk by chunk); index: run K0;
+// decode: run the decode kernels; pcm_dst: copy PCM back chunk by chunk.
 int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint8_t *pcm_dst, uint32_t *launches_out)
 {
     finish_timing(ctx);          // the events are about to be re-recorded
     const double t_enter = now_ms();
     const int n_dev = (int)ctx->devs.size();
-    uint32_t launches = 0, chunks_total = 0;
     // Zero-copy output: when the caller's buffer is page-locked and mapped (alacgpu_host_alloc, or any
     // cudaHostAlloc / cudaHostRegister'ed range) and the pack stage is fused, the pack warps write the
     // PCM straight into it over PCIe while the frames are still being decoded; there is no device PCM
     // copy and no D2H stage.
-    // chunk size: as much as possible in flight at once when the bytes are already resident;
-    // ~kSlots chunks when streaming from the host so copies and kernels overlap
-    static const uint64_t kf_min = getenv("ALACGPU_KF_MIN") ? strtoull(getenv("ALACGPU_KF_MIN"), nullptr, 10) : kFrameLaneMinFrames;
-    auto frame_lanes_for = [&](const Device &d) {
-        if (ctx->opts.flags & (ALACGPU_FLAG_NO_FRAME_LANES | ALACGPU_FLAG_NO_FUSION)) return false;
-        if (ctx->opts.flags & ALACGPU_FLAG_FORCE_FRAME_LANES) return true;
-        return d.f_hi - d.f_lo >= kf_min;
-    };
-    auto chunk_frames_for = [&](const Device &d) {
-        const uint64_t n_local = d.f_hi - d.f_lo;
-        const bool kf = frame_lanes_for(d);
-        const uint32_t cap = kf ? kFrameLaneMaxChunk : kMaxChunkFrames;
-        uint32_t cf = ctx->opts.chunk_frames;
-        if (!cf) {
-            if (stage) cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
-            else cf = (uint32_t)std::min<uint64_t>(n_local, cap);
-        }
-        return std::min<uint32_t>((cf + 31u) & ~31u, cap);
-    };
     bool all_fully_fused = !stage;
     for (const Device &d : ctx->devs)
-        if (d.f_hi > d.f_lo && (chunk_frames_for(d) > kFullFusionMaxFrames || frame_lanes_for(d))) all_fully_fused = false;
-    uint8_t *zc = nullptr;
-    if (pcm_dst && decode && all_fully_fused && !(ctx->opts.flags & (ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_PACK_FUSION | ALACGPU_FLAG_NO_ZERO_COPY))) {
+        if (d.f_hi > d.f_lo && (chunk_frames_for(ctx, d, stage) > kFullFusionMaxFrames || frame_lanes_for(ctx, d))) all_fully_fused = false;
+    PipeArgs pa{stage, index, decode, pcm_dst, nullptr, false, 0};
+    if (pcm_dst) {
         cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, pcm_dst) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-            zc = static_cast<uint8_t *>(at.devicePointer);
-        else
+        if (cudaPointerGetAttributes(&at, pcm_dst) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+            pa.dst_pinned = true;
+            if (decode && all_fully_fused && at.devicePointer &&
+                !(ctx->opts.flags & (ALACGPU_FLAG_NO_FUSION | ALACGPU_FLAG_NO_PACK_FUSION | ALACGPU_FLAG_NO_ZERO_COPY)))
+                pa.zc = static_cast<uint8_t *>(at.devicePointer);
+        } else {
             cudaGetLastError();
+        }
     }
     if (pcm_dst && decode) {       // alignment gaps between tracks are zero bytes in the layout (copies skip them)
         uint64_t end = 0;
@@ -613,97 +888,29 @@ int32_t run_pipeline(alacgpu_ctx *ctx, bool stage, bool index, bool decode, uint
             end = ht.pcm_off + ht.pcm_len;
         }
     }
-    for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        const uint64_t n_local = d.f_hi - d.f_lo;
-        if (!n_local) continue;
-        CU(cudaSetDevice(d.id));
-        const uint32_t cf = chunk_frames_for(d);
-        d.frame_lanes = frame_lanes_for(d);
-        static const bool no_taper = getenv("ALACGPU_NO_TAPER") != nullptr;
-        build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper && !d.frame_lanes);
-        const size_t n_chunks = d.chunks.size();
-        // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
-        d.slots_n = kSlots;
-        if (d.frame_lanes)
-            d.slots_n = (int)std::max<uint64_t>(3, std::min<uint64_t>(kSlots, kFrameLanePlaneBudget / ((uint64_t)cf * d.ns * 4u)));
-        const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
-        if (decode)
-            for (int s = 0; s < slots_used; s++) {
-                if (d.frame_lanes) {
-                    CU(d.slots[s].planes.reserve((size_t)cf * d.ns + 64u));          // one row per frame (channel A)
-                    CU(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
-                } else {
-                    CU(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
-                    CU(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
-                    CU(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
-                }
-            }
-        get_event(d, kEvBase + n_chunks * kEvPerChunk);          // create every event up front
-        CU(cudaEventRecord(d.events[0], d.slots[0].st));
-        for (int s = 1; s < slots_used; s++) CU(cudaStreamWaitEvent(d.slots[s].st, d.events[0], 0));
-        if (pcm_dst && !zc) {
-            CU(cudaStreamWaitEvent(d.st_d2h, d.events[0], 0));
-            CU(cudaEventRecord(d.events[2], d.st_d2h));
-        }
-        for (size_t ci = 0; ci < n_chunks; ci++) {
-            const Chunk &c = d.chunks[ci];
-            Slot &s = d.slots[ci % (size_t)d.slots_n];
-            const size_t ev = kEvBase + ci * kEvPerChunk;
-            if (stage) {
-                for (uint32_t k = c.copy_lo; k < c.copy_hi; k++)
-                    CU(cudaMemcpyAsync(d.arena.p + d.copies[k].dst, d.copies[k].src, d.copies[k].len,
-                                       cudaMemcpyHostToDevice, d.st_h2d));
-                CU(cudaEventRecord(d.events[ev + 5], d.st_h2d));
-                CU(cudaStreamWaitEvent(s.st, d.events[ev + 5], 0));
-            }
-            int32_t r = issue_chunk(ctx, d, c, s, index, decode, ev, &launches, zc, stage, stage && ci < 3);
-            if (r) return r;
-            if (pcm_dst && !zc && decode && c.pcm_hi > c.pcm_lo) {
-                CU(cudaStreamWaitEvent(d.st_d2h, d.events[ev + 4], 0));
-                CU(cudaMemcpyAsync(pcm_dst + c.pcm_lo, d.pcm.p + (c.pcm_lo - d.pcm_lo), c.pcm_hi - c.pcm_lo,
-                                   cudaMemcpyDeviceToHost, d.st_d2h));
-            }
-            chunks_total++;
-        }
-        // join: slot 0 waits for the last chunk of every other slot, then stamps the end
-        for (size_t ci = n_chunks > (size_t)d.slots_n ? n_chunks - (size_t)d.slots_n : 0; ci < n_chunks; ci++)
-            if (ci % (size_t)d.slots_n != 0) CU(cudaStreamWaitEvent(d.slots[0].st, d.events[kEvBase + ci * kEvPerChunk + 4], 0));
-        CU(cudaEventRecord(d.events[1], d.slots[0].st));
-        if (pcm_dst && !zc) CU(cudaEventRecord(d.events[3], d.st_d2h));
+    // one issuing thread per device (a single device runs on the caller's thread)
+    std::vector<DevRun> runs(n_dev);
+    if (n_dev == 1) {
+        run_device(ctx, ctx->devs[0], pa, runs[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_dev; g++) th.emplace_back([&, g] { run_device(ctx, ctx->devs[g], pa, runs[g]); });
+        for (std::thread &t : th) t.join();
     }
-    // ---- wait + timings --------------------------------------------------------
-    const double t_issued = now_ms();
-    double t_synced = 0;
-    uint32_t faults = 0;
+    uint32_t launches = 0, chunks_total = 0, faults = 0;
     for (int g = 0; g < n_dev; g++) {
-        Device &d = ctx->devs[g];
-        if (d.f_hi == d.f_lo) continue;
-        CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.slots[0].st));
-        if (pcm_dst && !zc) CU(cudaStreamSynchronize(d.st_d2h));
-        if (stage) CU(cudaStreamSynchronize(d.st_h2d));
-        t_synced = now_ms();
-        if (stage || index) d.resident = true;
-        if (stage) d.arena_staged = d.arena_used;
-        if (decode) { d.decoded = true; d.pcm_resident = !zc; }     // zero-copy output leaves no PCM in HBM
-        if (index || decode) {
-            uint32_t sc[2] = {0, 0};                                   // [0] K0 size mismatches, [1] FS_INTERNAL frames
-            CU(cudaMemcpy(sc, d.scalars.p, sizeof sc, cudaMemcpyDeviceToHost));
-            if (sc[0]) return fail(ctx, ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size");
-            if (sc[1]) {
-                faults += sc[1];
-                CU(cudaMemset(reinterpret_cast<uint32_t *>(d.scalars.p) + 1, 0, sizeof(uint32_t)));
-            }
-        }
+        if (runs[g].rc != ALACGPU_OK) return fail(ctx, runs[g].rc, runs[g].err.c_str());
+        launches += runs[g].launches;
+        chunks_total += runs[g].chunks;
+        faults += runs[g].faults;
     }
     ctx->internal_faults = faults;
     if (stage)                        // every byte is in HBM now: the host memory is no longer borrowed
         for (HostTrack &ht : ctx->tracks) { ht.staged = true; ht.mdat = nullptr; }
     if (getenv("ALACGPU_HOST_TIMING"))
-        fprintf(stderr, "[alacgpu] run_pipeline: issue %.3f ms, wait %.3f ms, after %.3f ms\n", t_issued - t_enter, t_synced - t_issued, now_ms() - t_synced);
+        fprintf(stderr, "[alacgpu] run_pipeline: %.3f ms\n", now_ms() - t_enter);
     ctx->timing_pending = true;
-    ctx->tp_stage = stage; ctx->tp_index = index; ctx->tp_decode = decode; ctx->tp_d2h = pcm_dst != nullptr; ctx->tp_zc = zc != nullptr;
+    ctx->tp_stage = stage; ctx->tp_index = index; ctx->tp_decode = decode; ctx->tp_d2h = pcm_dst != nullptr; ctx->tp_zc = pa.zc != nullptr;
     ctx->timing.chunks = chunks_total;
     if (launches_out) *launches_out = launches;
     ctx->have_status = false;
@@ -794,6 +1001,8 @@ int32_t alacgpu_create(const int32_t *device_ids, int32_t n_devices, const alacg
         if (id < 0 || id >= count) { delete ctx; return ALACGPU_ERR_NO_DEVICE; }
         ctx->devs.emplace_back();
         ctx->devs.back().id = id;
+        ctx->devs.back().h2d_prog.reset(new Progress());
+        ctx->devs.back().k_prog.reset(new Progress());
     }
     for (Device &d : ctx->devs) {
         bool ok = cudaSetDevice(d.id) == cudaSuccess &&
@@ -821,6 +1030,8 @@ int32_t alacgpu_destroy(alacgpu_ctx *ctx)
         d.expect_len.release(); d.frame_off.release(); d.scalars.release(); d.pcm.release();
         for (Slot &s : d.slots) { s.planes.release(); s.perm.release(); s.progress.release(); s.kf.release(); if (s.st) cudaStreamDestroy(s.st); }
         for (cudaEvent_t e : d.events) cudaEventDestroy(e);
+        d.ring_in.release();
+        d.ring_out.release();
         if (d.st_h2d) cudaStreamDestroy(d.st_h2d);
         if (d.st_d2h) cudaStreamDestroy(d.st_d2h);
     }

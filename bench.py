@@ -671,6 +671,18 @@ def run_ours(args):
                                     "host_buffers": "plain pageable memory (numpy) for both mdat and PCM"}
         if world == 1 and not single and args.latency_steps > 0 and name == "config4":
             line["latency_legs"] = {k: latency_leg(k, args, local) for k in ("config1", "config2", "config3")}
+        if world > 1 and not args.no_multidev_check:
+            # the drop-in C# API can only use the in-library form of multi-GPU (ONE alacgpu context over several
+            # devices); prove it on this box next to the per-rank numbers: tests/_multidev_case.py decodes a small
+            # batch through one context over GPUs 0 and 1 and compares it with the oracle byte for byte
+            import subprocess
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_multidev_case.py"), "0", "1"],
+                                   capture_output=True, text=True, timeout=600)
+                line["config"]["multi_device_context_check"] = ("ok: one context over GPUs 0,1 == oracle" if r.returncode == 0 and
+                                                                "multidev case ok" in r.stdout else "FAILED: " + (r.stdout + r.stderr)[-300:])
+            except Exception as e:          # noqa: BLE001
+                line["config"]["multi_device_context_check"] = f"not run: {e}"
         if not args.no_cpu:
             cores = host_cores()
             _, _, dt0 = cpu_decode_rate(corpus, 8, cores)
@@ -710,6 +722,7 @@ def main():
                     help="ALACGPU_FLAG_* bits: 2 no fusion, 4 no pack fusion, 8 no zero-copy output, 0x40 no frame lanes, 0x80 force frame lanes")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--single-process", action="store_true", help="one process, ONE alacgpu context over --gpus devices")
+    ap.add_argument("--no-multidev-check", action="store_true", help="N>1: skip the one-context-over-two-GPUs parity check on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

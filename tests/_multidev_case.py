@@ -24,6 +24,22 @@ def main():
     for t, o_, l_ in zip(tracks, off, ln):
         ref, _, _ = oracle.decode_track(oracle.cfg_from(t.cfg), t.mdat, t.stsz)
         assert pcm[int(o_):int(o_ + l_)].tobytes() == ref, "PCM differs from the oracle"
+    if len(devices) > 1:
+        # a multi-device context refuses tracks once its tracks are staged (alacgpu.h, alacgpu_add_track)
+        from alac.net_b200 import AlacGpuError
+        with BatchDecoder(devices=devices) as dec:
+            dec.add_track(tracks[0].cfg, tracks[0].mdat, tracks[0].stsz)
+            dec.prepare()
+            try:
+                dec.add_track(tracks[1].cfg, tracks[1].mdat, tracks[1].stsz)
+                raise SystemExit("a staged multi-device context accepted another track")
+            except AlacGpuError as e:
+                assert e.code == -7, e
+            dec.clear()
+            dec.add_track(tracks[1].cfg, tracks[1].mdat, tracks[1].stsz)
+            pcm, off, ln, status = dec.decode_all()
+            ref, _, _ = oracle.decode_track(oracle.cfg_from(tracks[1].cfg), tracks[1].mdat, tracks[1].stsz)
+            assert pcm[int(off[0]):int(off[0] + ln[0])].tobytes() == ref
     print("multidev case ok")
 
 

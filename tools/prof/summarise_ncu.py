@@ -3,6 +3,8 @@
 
     python tools/prof/summarise_ncu.py launches gpurun_out/launches.csv  > profiles/rN_launches.md
     python tools/prof/summarise_ncu.py full gpurun_out/prof_x.ncu-rep    > profiles/rN_x.md
+    python tools/prof/summarise_ncu.py issue gpurun_out/prof_x.ncu-rep <workload> [profiles/issue.json profiles/traffic.json]
+        integer-issue roofline of every captured kernel (merged into the two JSON files bench.py reads)
 """
 import csv
 import io
@@ -62,5 +64,60 @@ def launches(path):
         print(f"| {k} | {len(v)} | {sum(v) / len(v):.1f} | {sum(v):.1f} | {100 * sum(v) / total:.1f} % |")
 
 
+def issue(path, workload, issue_json=None, traffic_json=None):
+    """Issue-slot accounting per kernel name (launches of one name are summed): warp instructions executed
+    against the issue slots of the launch (4 sub-partitions x SMs x elapsed cycles), pipe shares, occupancy,
+    and the share of issue-active cycles lost to instruction fetch."""
+    import json
+    out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    num = lambda r, m: float(r[hdr.index(m)].replace(",", "")) if m in hdr and r[hdr.index(m)] not in ("", "n/a") else 0.0
+    unit = lambda m: rows[1][hdr.index(m)] if m in hdr else ""
+    to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("alacgpu::", "").split("<")[0]
+        a = agg.setdefault(name, {"launches": 0, "inst": 0.0, "slots": 0.0, "ms": 0.0, "dram": 0.0, "w": []})
+        cyc = num(r, "sm__cycles_elapsed.max")
+        sms = num(r, "launch__sm_count") or 148.0
+        dur = num(r, "gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(unit("gpu__time_duration.sum"), 1.0)
+        a["launches"] += 1
+        a["inst"] += num(r, "smsp__inst_executed.sum")
+        a["slots"] += 4.0 * sms * cyc
+        a["ms"] += dur
+        a["dram"] += num(r, "dram__bytes_read.sum") * to_bytes.get(unit("dram__bytes_read.sum"), 1.0) + \
+            num(r, "dram__bytes_write.sum") * to_bytes.get(unit("dram__bytes_write.sum"), 1.0)
+        a["w"].append((dur, {
+            "alu_pipe_pct": num(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct": num(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "stall_no_instruction": num(r, STALL_PREFIX + "no_instruction_per_issue_active.ratio"),
+            "registers": num(r, "launch__registers_per_thread"),
+        }))
+    res, traf = {}, {}
+    for name, a in agg.items():
+        tot = sum(d for d, _ in a["w"]) or 1.0
+        blk = {k: sum(d * m[k] for d, m in a["w"]) / tot for k in a["w"][0][1]}
+        blk.update({"launches_captured": a["launches"], "inst_executed": a["inst"], "issue_slots": a["slots"],
+                    "issue_frac": a["inst"] / a["slots"] if a["slots"] else None, "capture_ms": a["ms"],
+                    "source": path.split("/")[-1]})
+        res[name] = blk
+        traf[name] = a["dram"]
+        print(name, json.dumps(blk))
+    for fn, val in ((issue_json, res), (traffic_json, traf)):
+        if fn:
+            try:
+                cur = json.load(open(fn))
+            except Exception:
+                cur = {}
+            cur.setdefault(workload, {}).update(val)
+            json.dump(cur, open(fn, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"full": full, "launches": launches}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "issue":
+        issue(*sys.argv[2:])
+    else:
+        {"full": full, "launches": launches}[sys.argv[1]](sys.argv[2])
