@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libalacgpu.so")
+# ALACGPU_LIB selects another build of the same ABI (tests: libalacgpu_checked.so, the bounds-asserting build)
+LIB_PATH = os.environ.get("ALACGPU_LIB") or os.path.join(_HERE, "libalacgpu.so")
 
 OK = 0
 ERR_NAMES = {

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB_GPU = os.path.join(HERE, "libalacgpu.so")
+LIB_GPU_CHECKED = os.path.join(HERE, "libalacgpu_checked.so")   # -DALACGPU_CHECKED: bounds assertions in every kernel
 LIB_HOST = os.path.join(HERE, "libalacnet_host.so")
 
 CU_SOURCES = ["k0_index.cu", "k12_decode.cu", "k3_stereo.cu", "kf_frame.cu", "runtime.cu"]
@@ -29,7 +30,11 @@ def _newer(target: str, sources: list[str]) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_gpu(force: bool = False, verbose: bool = False) -> str:
+def build_gpu(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    """libalacgpu.so, or (checked) libalacgpu_checked.so: the same sources with -DALACGPU_CHECKED, the stand-in for
+    compute-sanitizer (closed on this GPU pool) that the -m gpu tests run the fuzz / malformed-stream cases under."""
+    LIB_GPU = LIB_GPU_CHECKED if checked else globals()["LIB_GPU"]
+    OBJ_DIR = globals()["OBJ_DIR"] + ("_checked" if checked else "")
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
     deps.append(os.path.join(ROOT, "include", "alacgpu.h"))
@@ -37,11 +42,11 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
         # one object per source, compiled side by side (the frame-lane kernels alone take ~40 s), then one link
         from concurrent.futures import ThreadPoolExecutor
         os.makedirs(OBJ_DIR, exist_ok=True)
-        extra = (["-DALACGPU_CHECKED"] if os.environ.get("ALACGPU_CHECKED") == "1" else [])
+        extra = ["-DALACGPU_CHECKED"] if checked else []
 
         def compile_one(src: str) -> str:
             obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-            if force or _newer(obj, [src] + [d for d in deps if not d.endswith(".cu")]) or extra:
+            if force or _newer(obj, [src] + [d for d in deps if not d.endswith(".cu")]):
                 cmd = ["nvcc", *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
                 if verbose:
                     cmd.insert(1, "-Xptxas=-v")
@@ -92,7 +97,9 @@ def build_cli(force: bool = False) -> str:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
-    build_gpu(force, verbose)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=2) as ex:           # release and checked builds side by side
+        list(ex.map(lambda c: build_gpu(force, verbose, checked=c), (False, True)))
     build_host(force)
     build_cli(force)
 

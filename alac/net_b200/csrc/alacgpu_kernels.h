@@ -64,6 +64,7 @@ struct ChunkArgs {
                                    // [8 ..] scratch of the sort (class histograms and cursors)
     uint32_t kf_cap;               // entries per padded list: n + kKfClasses * 31 rounded up to 32
     uint32_t *bstart;              // per frame slot: bit offset (from the frame start) where channel B's Rice stream starts
+    uint32_t kf_row;               // bytes per frame of the channel-A plane: ns x 2 (only 16-bit tracks on the device) or ns x 4
 };
 cudaError_t launch_k1(const ChunkArgs &a, int lanes_per_warp, cudaStream_t st, uint32_t *launches);
 cudaError_t launch_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launches);   // K2 / K12 work list

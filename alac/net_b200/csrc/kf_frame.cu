@@ -455,7 +455,9 @@ struct LaneLpc {
         rneg = (1u << quant) - 1u;                          // see k2_lpc.cuh lpc_warp
         sh = (32 - rss) & 31;
     }
-    // sample i with residual e; `hv`: the lane really has a sample this round (state moves only then)
+    // sample i with residual e.  `hv`: the lane really has a sample this round; a lane without one has finished
+    // its channel (the predictor only runs when every unfinished lane holds a residual), so its state may move
+    // freely -- only its coefficient update is switched off, to keep the arithmetic in range
     __device__ __forceinline__ int32_t step(const int32_t e, const uint32_t i, const bool hv)
     {
         if constexpr (M == 0) {
@@ -464,7 +466,7 @@ struct LaneLpc {
             const int32_t x = (int32_t)((uint32_t)H[0] + (uint32_t)e);
             int32_t o = (int32_t)((uint32_t)x << sh) >> sh;
             o = i == 0 ? e : o;                                         // :259-260
-            H[0] = hv ? o : H[0];
+            H[0] = o;
             return o;
         } else {
             const bool main = i > (uint32_t)M;                          // warm-up covers i = 1..M (:284-293)
@@ -483,8 +485,8 @@ struct LaneLpc {
             int32_t o = (int32_t)((uint32_t)x << sh) >> sh;             // :309-310
             o = i == 0 ? e : o;                                         // first sample copies (:259-260)
 #pragma unroll
-            for (int j = M; j > 0; --j) H[j] = hv ? H[j - 1] : H[j];
-            H[0] = hv ? o : H[0];
+            for (int j = M; j > 0; --j) H[j] = H[j - 1];
+            H[0] = o;
             return o;
         }
     }
@@ -505,7 +507,7 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
     constexpr int ch = kB ? 1 : 0;
     bool work = valid && in_chunk && d.status == FS_OK;             // phase B: channel A may have failed in phase A
     // (checked build) the frame's channel-A row lies inside the slot's plane
-    if (work && !ALACGPU_CHECK(a.check, ((uint64_t)slot + 1u) * a.ns * 4u <= a.plane_bytes && d.n <= a.ns, CK_PLANE)) work = false;
+    if (work && !ALACGPU_CHECK(a.check, ((uint64_t)slot + 1u) * a.kf_row <= a.plane_bytes && d.n <= a.ns, CK_PLANE)) work = false;
     const uint32_t n = work ? (uint32_t)d.n : 0u;
     const bool is24 = cfg.sample_size == 24;
     const bool stereo = (d.flags & FF_STEREO) != 0;
@@ -537,7 +539,7 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
 
     // output: PCM, or (phase A of a stereo element) the channel-A plane row, 2 bytes per sample for
     // 16-bit tracks and 4 for 24-bit ones
-    uint8_t *const plane_row = reinterpret_cast<uint8_t *>(a.planes) + (uint64_t)slot * a.ns * 4u;
+    uint8_t *const plane_row = reinterpret_cast<uint8_t *>(a.planes) + (uint64_t)slot * a.kf_row;
     OutStage out;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(wsm + kRingBytes * 32u) + (uint32_t)lane * kStageStride;
     const bool to_plane = !kB && stereo_w;
@@ -783,14 +785,17 @@ cudaError_t launch_kf_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launch
 // The frame-lane kernels live on shared memory (three lane-private rings per lane) and barely use L1: ask for
 // the largest shared-memory carve-out so that the register file, not the carve-out, bounds the blocks per SM.
 template <bool kB>
-static cudaError_t kf_attributes(int *blocks_per_sm)
+static cudaError_t kf_attributes(int *blocks_per_sm, int *smem_bytes)
 {
-    const int smem = 2 * (int)(kB ? kKfWarpSmemB : kKfWarpSmemA);
+    // ALACGPU_KF_PAD_A / _B (KB): extra dynamic shared memory per block, i.e. fewer resident blocks per SM (tuning runs)
+    static const int pad = getenv(kB ? "ALACGPU_KF_PAD_B" : "ALACGPU_KF_PAD_A") ? atoi(getenv(kB ? "ALACGPU_KF_PAD_B" : "ALACGPU_KF_PAD_A")) * 1024 : 0;
+    const int smem = 2 * (int)(kB ? kKfWarpSmemB : kKfWarpSmemA) + pad;
     if (cudaError_t e = cudaFuncSetAttribute(kf_frames<kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) return e;
     if (cudaError_t e = cudaFuncSetAttribute(kf_frames<kB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return e;
     int nb = 0;
     if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kf_frames<kB>, kKfThreads, smem)) return e;
     *blocks_per_sm = std::max(nb, 1);
+    *smem_bytes = smem;
     static const bool dbg = getenv("ALACGPU_DEBUG_OCC") != nullptr;
     if (dbg) {
         cudaFuncAttributes fa{};
@@ -804,12 +809,12 @@ static cudaError_t kf_attributes(int *blocks_per_sm)
 cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    int per_sm = 1;
-    if (cudaError_t e = kf_attributes<false>(&per_sm)) return e;
+    int per_sm = 1, smem = 0;
+    if (cudaError_t e = kf_attributes<false>(&per_sm, &smem)) return e;
     const uint32_t nseg = kf_segments();
     // persistent warps: as many blocks as fit the machine at once (fewer for a chunk that cannot fill it)
     const uint32_t blocks = std::min<uint32_t>(nseg * (uint32_t)per_sm, a.kf_cap / kKfThreads);
-    kf_frames<false><<<blocks, kKfThreads, 2 * kKfWarpSmemA, st>>>(a, nseg);
+    kf_frames<false><<<blocks, kKfThreads, smem, st>>>(a, nseg);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -817,11 +822,11 @@ cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 cudaError_t launch_kf_b(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
-    int per_sm = 1;
-    if (cudaError_t e = kf_attributes<true>(&per_sm)) return e;
+    int per_sm = 1, smem = 0;
+    if (cudaError_t e = kf_attributes<true>(&per_sm, &smem)) return e;
     const uint32_t nseg = kf_segments();
     const uint32_t blocks = std::min<uint32_t>(nseg * (uint32_t)per_sm, a.kf_cap / kKfThreads);
-    kf_frames<true><<<blocks, kKfThreads, 2 * kKfWarpSmemB, st>>>(a, nseg);
+    kf_frames<true><<<blocks, kKfThreads, smem, st>>>(a, nseg);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -53,8 +53,11 @@ constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by t
 // frames than lanes (148 SMs x 512 lanes), so every chunk is decoded one lane per frame and channel, with
 // chunks big enough that the class padding of the work lists stays small
 constexpr uint64_t kFrameLaneMinFrames = 65536;
-constexpr uint32_t kFrameLaneMaxChunk = 262144;
-constexpr uint64_t kFrameLanePlaneBudget = 16ull << 30;   // bytes of channel-A planes over all slots in flight
+constexpr uint32_t kFrameLaneMaxChunk = 8u << 20;
+// bytes of channel-A planes over all slots in flight.  Resident inputs: one chunk as big as this allows (a frame
+// lane's task is 32 frames x 4096 samples, ~5 ms: the fewer launches, the less of the machine idles in their
+// tails); inputs streamed in: chunks of 1/16 of the frames, as many slots as fit
+constexpr uint64_t kFrameLanePlaneBudget = 48ull << 30;
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 constexpr uint64_t kRingSlotBytes = 16ull << 20;   // one slot of the page-locked staging rings (host_staging.h)
 
@@ -146,6 +149,7 @@ struct Device {
     uint64_t pcm_lo = 0, pcm_hi = 0;  // global byte range held by `pcm` (pcm_lo 256-aligned)
     uint64_t pcm_first = 0;           // global offset of the first byte this shard produces
     uint32_t ns = 64;                 // plane row stride (samples): multiple of 32, plus 32 so rows are not 16 KiB apart
+    uint32_t kf_row = 256;            // frame-lane path: bytes per frame of the channel-A plane (ns x 2 without 24-bit tracks)
     std::vector<FrameRef> h_refs;
     std::vector<HostCopy> track_copies;   // one per (track, device): host bytes -> arena
     std::vector<HostCopy> copies;         // the same bytes split at chunk boundaries
@@ -356,6 +360,14 @@ int32_t build_plan(alacgpu_ctx *ctx)
         }
         d.arena_used = used;
         d.ns = std::max<uint32_t>((ctx->max_sf + 31u) & ~31u, 32u) + 32u;
+        {
+            bool any24 = false;
+            for (uint32_t t = 0; t < n_tracks; t++) {
+                const HostTrack &ht = ctx->tracks[t];
+                if (ht.first_frame < d.f_hi && ht.first_frame + ht.n_frames > d.f_lo && ht.cfg.sample_size == 24) any24 = true;
+            }
+            d.kf_row = d.ns * (any24 ? 4u : 2u);
+        }
         // PCM byte range of the shard (contiguous in the global layout)
         if (n_local) {
             d.pcm_first = ctx->frame_off[d.f_lo];
@@ -468,9 +480,13 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ChunkArgs ca{};
     ca.arena = d.arena.p; ca.refs = d.refs.p; ca.cfgs = d.cfgs.p; ca.desc = d.desc.p; ca.coefs = d.coefs.p;
     ca.frame_off = d.frame_off.p; ca.planes = s.planes.p; ca.pcm = d.pcm.p; ca.pcm_base = d.pcm_lo;
-    ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf;
+    ca.ns = d.ns; ca.f0 = c.f0; ca.n = c.n; ca.max_sf = ctx->max_sf; ca.kf_row = d.kf_row;
     ca.perm = s.perm.p; ca.perm_count = s.perm.p + 4u * (size_t)d.chunk_frames + 1024u;
     ca.faults = reinterpret_cast<uint32_t *>(d.scalars.p) + 1;
+    ca.check = reinterpret_cast<uint32_t *>(d.scalars.p) + 2;          // ALACGPU_CHECKED build: extents of every buffer
+    ca.arena_bytes = d.arena_used + kArenaTail;
+    ca.plane_bytes = (uint64_t)s.planes.cap * sizeof(int32_t);
+    ca.pcm_bytes = pcm_override ? ctx->total_pcm : d.pcm_hi - d.pcm_lo + 64;
     {
         // four-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
         // streams from order 17 up (configs[1], final r1 kernels: 2.65 ms; from 25 up 2.61, from 21 up 3.24,
@@ -502,6 +518,7 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
         ka.arena = d.arena.p; ka.refs = d.refs.p; ka.cfgs = d.cfgs.p; ka.desc = d.desc.p; ka.coefs = d.coefs.p;
         ka.expect_len = d.expect_len.p; ka.mismatch = reinterpret_cast<uint32_t *>(d.scalars.p);
         ka.f0 = c.f0; ka.n = c.n;
+        ka.arena_bytes = ca.arena_bytes; ka.check = ca.check;
         CUI(launch_k0(ka, s.st, launches));
     }
     CUI(cudaEventRecord(get_event(d, ev + 1), s.st));
@@ -641,6 +658,19 @@ bool frame_lanes_for(const alacgpu_ctx *ctx, const Device &d)
 
 // chunk size: as much as possible in flight at once when the bytes are already resident; ~kSlots chunks when
 // streaming from the host so copies and kernels overlap
+// bytes the channel-A planes of the frame-lane path may take on this device: the budget, or what is left of
+// HBM (planes already allocated for earlier calls count as available)
+uint64_t plane_budget(const Device &d)
+{
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return kFrameLanePlaneBudget; }
+    uint64_t have = 0;
+    for (const Slot &s : d.slots) have += (uint64_t)s.planes.cap * sizeof(int32_t);
+    const uint64_t avail = (uint64_t)free_b + have;
+    const uint64_t keep = 6ull << 30;                       // work lists, status words, the caller's own allocations
+    return std::min<uint64_t>(kFrameLanePlaneBudget, avail > keep ? avail - keep : 0);
+}
+
 uint32_t chunk_frames_for(const alacgpu_ctx *ctx, const Device &d, bool stage)
 {
     const uint64_t n_local = d.f_hi - d.f_lo;
@@ -648,8 +678,17 @@ uint32_t chunk_frames_for(const alacgpu_ctx *ctx, const Device &d, bool stage)
     const uint32_t cap = kf ? kFrameLaneMaxChunk : kMaxChunkFrames;
     uint32_t cf = ctx->opts.chunk_frames;
     if (!cf) {
-        if (stage) cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
-        else cf = (uint32_t)std::min<uint64_t>(n_local, cap);
+        if (stage) {
+            cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
+        } else if (kf) {
+            // the whole shard in one chunk if its plane fits, else as few chunks as two alternating slots allow
+            const uint64_t budget = std::max<uint64_t>(plane_budget(d), 2ull * 32768 * d.kf_row);
+            uint64_t chunks = 1;
+            if (n_local * d.kf_row > budget) chunks = (n_local * d.kf_row + budget / 2 - 1) / (budget / 2);
+            cf = (uint32_t)std::min<uint64_t>((n_local + chunks - 1) / chunks, cap);
+        } else {
+            cf = (uint32_t)std::min<uint64_t>(n_local, cap);
+        }
     }
     return std::min<uint32_t>((cf + 31u) & ~31u, cap);
 }
@@ -676,12 +715,12 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
     // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
     d.slots_n = kSlots;
     if (d.frame_lanes)
-        d.slots_n = (int)std::max<uint64_t>(3, std::min<uint64_t>(kSlots, kFrameLanePlaneBudget / ((uint64_t)cf * d.ns * 4u)));
+        d.slots_n = (int)std::max<uint64_t>(2, std::min<uint64_t>(kSlots, plane_budget(d) / std::max<uint64_t>(1, (uint64_t)cf * d.kf_row)));
     const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
     if (decode)
         for (int s = 0; s < slots_used; s++) {
             if (d.frame_lanes) {
-                CUD(d.slots[s].planes.reserve((size_t)cf * d.ns + 64u));          // one row per frame (channel A)
+                CUD(d.slots[s].planes.reserve(((size_t)cf * d.kf_row + 3u) / 4u + 64u));          // one row per frame (channel A)
                 CUD(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
             } else {
                 CUD(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
@@ -844,9 +883,16 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
     if (stage) d.arena_staged = d.arena_used;
     if (decode) { d.decoded = true; d.pcm_resident = !zc; }     // zero-copy output leaves no PCM in HBM
     if (index || decode) {
-        uint32_t sc[2] = {0, 0};                                   // [0] K0 size mismatches, [1] FS_INTERNAL frames
+        uint32_t sc[3] = {0, 0, 0};                                // [0] K0 size mismatches, [1] FS_INTERNAL frames, [2] bounds checks
         CUD(cudaMemcpy(sc, d.scalars.p, sizeof sc, cudaMemcpyDeviceToHost));
         if (sc[0]) { res.set_error(ALACGPU_ERR_STATE, "internal: host and device disagree on a frame's PCM size", cudaSuccess); return false; }
+        if (sc[2]) {                                               // only the ALACGPU_CHECKED build ever sets these
+            char msg[160];
+            snprintf(msg, sizeof msg, "checked build: bounds assertion failed, mask 0x%x (bit 0 arena, 1 plane, 2 list, 3 progress, 4 pcm, 5 ring, 6 frame)", sc[2]);
+            cudaMemset(reinterpret_cast<uint32_t *>(d.scalars.p) + 2, 0, sizeof(uint32_t));
+            res.set_error(ALACGPU_ERR_STATE, msg, cudaSuccess);
+            return false;
+        }
         if (sc[1]) {
             res.faults = sc[1];
             CUD(cudaMemset(reinterpret_cast<uint32_t *>(d.scalars.p) + 1, 0, sizeof(uint32_t)));
