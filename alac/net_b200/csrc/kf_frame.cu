@@ -221,6 +221,7 @@ struct OutStage {
         head = (uint32_t)((uintptr_t)dst & 15u);
         g = dst - head;
         s = saddr;
+        asm volatile("" : "+r"(s));     // keep the ring address in a register (ptxas otherwise re-derives it from %tid every sample)
         p = head;
         F = 0;
     }
@@ -292,6 +293,7 @@ struct PlaneRing {
     __device__ __forceinline__ void init(const uint8_t *row, uint32_t saddr, uint32_t bytes)
     {
         base = row; s = saddr; filled = 0; limit = (bytes + 15u) >> 4;
+        asm volatile("" : "+r"(s));
     }
     // `byte`: offset of the next sample to be read; a period reads at most 16 samples (64 bytes) and the
     // copies issued here are only waited for at the NEXT top-up: ask for two periods + the straddle
@@ -471,10 +473,16 @@ struct LaneLpc {
         } else {
             const bool main = i > (uint32_t)M;                          // warm-up covers i = 1..M (:284-293)
             const int32_t base = H[M];
-            const int32_t nsg = e < 0 ? 1 : -1;                         // -sign(err)
-            const int32_t sgbase = e < 0 ? (int32_t)(0u - (uint32_t)base) : base;
-            int32_t E = (main && hv) ? (e < 0 ? (int32_t)(0u - (uint32_t)e) : e) : 0;   // sign(err) * err
-            const uint32_t r = e < 0 ? rneg : 0u;
+            // sign(err) as arithmetic on the FMA pipe (the ALU pipe is the one this kernel saturates): with
+            // m = err >> 31 (0 or -1), sign = 2 m + 1, -sign = -2 m - 1
+            const int32_t m = e >> 31;
+            int32_t sg, nsg;
+            asm("mad.lo.s32 %0, %1, 2, 1;" : "=r"(sg) : "r"(m));
+            asm("mad.lo.s32 %0, %1, -2, -1;" : "=r"(nsg) : "r"(m));      // -sign(err)
+            const int32_t sgbase = (int32_t)((uint32_t)sg * (uint32_t)base);
+            const int32_t mag = (int32_t)((uint32_t)sg * (uint32_t)e);   // sign(err) * err
+            int32_t E = (main && hv) ? mag : 0;
+            const uint32_t r = (uint32_t)m & rneg;
             uint32_t acc = 0;
             lpc_taps<M, M - 1>(c, H, E, acc, nsg, sgbase, r, q);
             const int32_t sum = (int32_t)(acc * (uint32_t)nsg);

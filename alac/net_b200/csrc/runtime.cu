@@ -49,10 +49,12 @@ constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
 constexpr int kSlots = 16;
 constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
-// Frame-lane path (kf_frame.cu): a device whose share of the batch holds at least this many frames has more
-// frames than lanes (148 SMs x 512 lanes), so every chunk is decoded one lane per frame and channel, with
-// chunks big enough that the class padding of the work lists stays small
-constexpr uint64_t kFrameLaneMinFrames = 65536;
+// Frame-lane path (kf_frame.cu): one lane per frame and channel from bitstream to PCM.  A lane's task is 32
+// frames x 4096 samples (~5 ms), so the path needs MANY tasks per SM before its tails stop mattering: measured
+// on B200 (16-bit stereo, resident inputs) 46.6 vs 62.9 Gsamples/s for the stream-lane kernels at 174 k frames,
+// 53 vs 66 at 678 k, 68.3 vs 66.4 at 2.71 M -- with 1.6x instead of 4.2x the algorithmic bytes in DRAM traffic.
+// A device whose share of the batch holds at least this many frames takes it.
+constexpr uint64_t kFrameLaneMinFrames = 1500000;
 constexpr uint32_t kFrameLaneMaxChunk = 8u << 20;
 // bytes of channel-A planes over all slots in flight.  Resident inputs: one chunk as big as this allows (a frame
 // lane's task is 32 frames x 4096 samples, ~5 ms: the fewer launches, the less of the machine idles in their
@@ -645,8 +647,8 @@ struct DevRun {             // what one device's pipeline run reports back
 
 uint64_t frame_lane_min_frames()
 {
-    static const uint64_t v = getenv("ALACGPU_KF_MIN") ? strtoull(getenv("ALACGPU_KF_MIN"), nullptr, 10) : kFrameLaneMinFrames;
-    return v;
+    const char *e = getenv("ALACGPU_KF_MIN");          // read per call: tests and tuning runs move the threshold
+    return e ? strtoull(e, nullptr, 10) : kFrameLaneMinFrames;
 }
 
 bool frame_lanes_for(const alacgpu_ctx *ctx, const Device &d)

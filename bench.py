@@ -103,6 +103,20 @@ def make_corpus(name: str, world: int, args) -> Corpus:
         return Corpus(uniq, np.arange(n) % u,
                       f"configs[3]: batch of {n} synthetic 16-bit stereo 44.1 kHz tracks x {252.0 * s:g} s decoded in one "
                       f"call ({u} distinct tracks, every replica staged separately in HBM)", name)
+    if name == "fixed":
+        # tuning runs: 16-bit stereo tracks whose frames all use predictor orders in --orders lo,hi
+        lo, hi = (int(x) for x in args.orders.split(","))
+        n = args.tracks or 32
+        u = max(1, min(args.unique, n))
+        uniq = []
+        for i in range(u):
+            seed = g.SEED_BASE + 5000 + i
+            rng = np.random.default_rng(seed)
+            cfg = g.TrackCfg(16, 2, 4096, 40, 10, 14, 44100)
+            ns = int(round(252.0 * s * 44100))
+            x = g.make_signal(seed, ns, 16, 44100, 2)
+            uniq.append(g.build_track(cfg, x, g.make_frames(rng, cfg, ns, True, orders=(lo, hi), quants=(1, 15), rice_mods=(1, 7))))
+        return Corpus(uniq, np.arange(n) % u, f"tuning: {n} 16-bit stereo tracks x {252.0 * s:g} s, predictor orders {lo}..{hi}", "fixed")
     if name == "config5":
         per = args.tracks_per_gpu or 1250
         n = args.tracks or per * world
@@ -601,7 +615,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         stage = {k: acc[k] / args.steps for k in acc}
         b_alg = comp_bytes + pcm_bytes
-        frame_lanes = (not (args.flags & 0x42)) and ((args.flags & 0x80) or n_frames // max(1, len(devices)) >= 65536)
+        frame_lanes = (not (args.flags & 0x42)) and ((args.flags & 0x80) or n_frames // max(1, len(devices)) >= int(os.environ.get("ALACGPU_KF_MIN", 1500000)))
         fused = not (args.flags & 2)
         if frame_lanes:
             dom_name, dom_sum = "kf_frames", stage["entropy_ms"] + stage["lpc_ms"]
@@ -710,6 +724,7 @@ def main():
     ap.add_argument("--tracks", type=int, default=0, help="tracks of config4 / config5 (0 = 1000 / 1250 per GPU)")
     ap.add_argument("--tracks-per-gpu", type=int, default=0)
     ap.add_argument("--unique", type=int, default=8, help="distinct tracks generated for config4")
+    ap.add_argument("--orders", default="0,31", help="workload `fixed`: predictor order range lo,hi of every frame")
     ap.add_argument("--unique-per-kind", type=int, default=1, help="distinct tracks per i mod 10 residue for config5")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-pageable-steps", type=int, default=2)
