@@ -174,6 +174,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.recording = False          # the thread runs through the warm-up (NVML's first queries are slow and were seen
+                                        # to stall the launching thread for 0.1-0.5 s); samples count from begin() on
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -199,17 +201,22 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
+                if self.recording:
+                    self.samples.append(mhz)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
             except Exception:
                 pass
             time.sleep(self.period)
+
+    def begin(self):
+        self.recording = True
 
     def finish(self):
         self._stop_evt.set()
@@ -547,11 +554,12 @@ def run_ours(args):
         return dec.timing()
 
     warm = max(3, args.warmup)
+    sampler = ClockSampler(devices[0], period=0.05)
+    sampler.start()
     for _ in range(warm):
         step()
-    sampler = ClockSampler(devices[0])
     barrier()
-    sampler.start()
+    sampler.begin()
     t0 = time.perf_counter()
     acc = {"index_ms": 0.0, "entropy_ms": 0.0, "lpc_ms": 0.0, "stereo_ms": 0.0, "kernels_ms": 0.0}
     launches = 0
@@ -634,6 +642,8 @@ def run_ours(args):
         dom_ms = path_ms * share if chunks > 1 else dom_sum
         achieved = b_alg / (dom_ms * 1e-3) / 1e9
         traffic = load_profile_json("traffic.json").get(name, {}).get(dom_name)
+        if isinstance(traffic, dict):       # captured on a smaller batch of the same workload: DRAM bytes scale with the frames
+            traffic = traffic["bytes"] * (n_frames / max(1, traffic["frames"]))
         issue = load_profile_json("issue.json").get(name, {}).get(dom_name)
         line = {
             "metric": METRIC, "value": samples_all / (wall_ms_max * 1e-3) / 1e6, "unit": UNIT,

@@ -3,8 +3,9 @@
 
     python tools/prof/summarise_ncu.py launches gpurun_out/launches.csv  > profiles/rN_launches.md
     python tools/prof/summarise_ncu.py full gpurun_out/prof_x.ncu-rep    > profiles/rN_x.md
-    python tools/prof/summarise_ncu.py issue gpurun_out/prof_x.ncu-rep <workload> [profiles/issue.json profiles/traffic.json]
-        integer-issue roofline of every captured kernel (merged into the two JSON files bench.py reads)
+    python tools/prof/summarise_ncu.py issue gpurun_out/prof_x.ncu-rep <workload> [profiles/issue.json profiles/traffic.json [frames]]
+        integer-issue roofline of every captured kernel (merged into the two JSON files bench.py reads); `frames` = frames
+        the captured launches decoded, so that bench.py can scale the DRAM traffic to the batch it runs
 """
 import csv
 import io
@@ -64,7 +65,7 @@ def launches(path):
         print(f"| {k} | {len(v)} | {sum(v) / len(v):.1f} | {sum(v):.1f} | {100 * sum(v) / total:.1f} % |")
 
 
-def issue(path, workload, issue_json=None, traffic_json=None):
+def issue(path, workload, issue_json=None, traffic_json=None, frames=None):
     """Issue-slot accounting per kernel name (launches of one name are summed): warp instructions executed
     against the issue slots of the launch (4 sub-partitions x SMs x elapsed cycles), pipe shares, occupancy,
     and the share of issue-active cycles lost to instruction fetch."""
@@ -103,8 +104,10 @@ def issue(path, workload, issue_json=None, traffic_json=None):
         blk.update({"launches_captured": a["launches"], "inst_executed": a["inst"], "issue_slots": a["slots"],
                     "issue_frac": a["inst"] / a["slots"] if a["slots"] else None, "capture_ms": a["ms"],
                     "source": path.split("/")[-1]})
+        if frames:
+            blk["frames_in_capture"] = int(frames)
         res[name] = blk
-        traf[name] = a["dram"]
+        traf[name] = {"bytes": a["dram"], "frames": int(frames)} if frames else a["dram"]
         print(name, json.dumps(blk))
     for fn, val in ((issue_json, res), (traffic_json, traf)):
         if fn:
