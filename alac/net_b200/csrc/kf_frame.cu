@@ -48,10 +48,12 @@ constexpr int kKfThreads = 64;                 // two warps per block: every str
 constexpr int kKfPeriod = 16;                  // iterations between ring top-ups / flushes
 constexpr uint32_t kStageStride = 144;         // bytes per lane: 128-byte ring + 16 (lanes 8 apart share banks: 4-way)
 constexpr uint32_t kStageRing = 128;
-constexpr uint32_t kARingStride = 272;         // channel-A ring: 256 bytes + 16
-constexpr uint32_t kARingBytes = 256;
+// channel-A ring of phase B: 256 bytes + 16 per lane when the device holds 24-bit tracks (4-byte plane samples),
+// 128 + 16 when it holds only 16-bit ones (a sixth block then fits the SM's shared memory)
+constexpr uint32_t kARingStride = 272;
+__host__ __device__ constexpr uint32_t kf_aring_stride(uint32_t kf_row, uint32_t ns) { return kf_row == ns * 2u ? 144u : kARingStride; }
 constexpr uint32_t kKfWarpSmemA = kRingBytes * 32 + kStageStride * 32;                 // 12800
-constexpr uint32_t kKfWarpSmemB = kKfWarpSmemA + kARingStride * 32;                    // 21504
+
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 
 // ---- classes ---------------------------------------------------------------------------------
@@ -290,34 +292,38 @@ struct PlaneRing {
     uint32_t s;          // shared-space address of the ring
     uint32_t filled;     // chunks requested so far
     uint32_t limit;      // chunks that hold samples of this frame
-    __device__ __forceinline__ void init(const uint8_t *row, uint32_t saddr, uint32_t bytes)
+    uint32_t mask;       // ring bytes - 1 (255 or 127)
+    uint32_t ahead;      // chunks requested beyond the one being read: two periods of samples + the straddle
+    __device__ __forceinline__ void init(const uint8_t *row, uint32_t saddr, uint32_t bytes, uint32_t ring_bytes)
     {
         base = row; s = saddr; filled = 0; limit = (bytes + 15u) >> 4;
+        mask = ring_bytes - 1u;
+        ahead = ring_bytes == 256u ? 10u : 6u;       // 256: 32 four-byte samples = 8 chunks (+2); 128: 32 two-byte samples = 4 (+2)
         asm volatile("" : "+r"(s));
     }
     // `byte`: offset of the next sample to be read; a period reads at most 16 samples (64 bytes) and the
     // copies issued here are only waited for at the NEXT top-up: ask for two periods + the straddle
     __device__ __forceinline__ void top_up(uint32_t byte)
     {
-        const uint32_t want = min((byte >> 4) + 10u, limit);
+        const uint32_t want = min((byte >> 4) + ahead, limit);
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const uint32_t go = filled < want ? 1u : 0u;
-            cp_async16_if(s + ((filled & 15u) << 4), base + ((uint64_t)filled << 4), go);
+            cp_async16_if(s + ((filled << 4) & mask), base + ((uint64_t)filled << 4), go);
             filled += go;
         }
     }
     __device__ __forceinline__ void prime()        // first two periods' worth, waited for by the caller
     {
-        for (; filled < min(10u, limit); ++filled) cp_async16(s + ((filled & 15u) << 4), base + ((uint64_t)filled << 4));
+        for (; filled < min(ahead, limit); ++filled) cp_async16(s + ((filled << 4) & mask), base + ((uint64_t)filled << 4));
     }
     __device__ __forceinline__ uint32_t get16(uint32_t byte) const
     {
         uint32_t v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(s + (byte & (kARingBytes - 1))) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(s + (byte & mask)) : "memory");
         return v;
     }
-    __device__ __forceinline__ uint32_t get32(uint32_t byte) const { return lds32(s + (byte & (kARingBytes - 1))); }
+    __device__ __forceinline__ uint32_t get32(uint32_t byte) const { return lds32(s + (byte & mask)); }
 };
 
 // ---- one entropy step with the residual left in a register ------------------------------------------
@@ -556,8 +562,9 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
              to_plane ? CK_PLANE : CK_PCM);
     PlaneRing ar;
     if (kB) {
-        ar.init(plane_row, (uint32_t)__cvta_generic_to_shared(wsm + kKfWarpSmemA) + (uint32_t)lane * kARingStride,
-                n * (is24 ? 4u : 2u));
+        const uint32_t astride = kf_aring_stride(a.kf_row, a.ns);
+        ar.init(plane_row, (uint32_t)__cvta_generic_to_shared(wsm + kKfWarpSmemA) + (uint32_t)lane * astride,
+                n * (is24 ? 4u : 2u), astride - 16u);
         if (work) ar.prime();
         cp_async_commit();
         cp_async_wait<0>();
@@ -667,7 +674,7 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
 // next segment that still has work (and stays there), which evens out the tail.  Nothing ever waits on
 // another warp: the schedule is only a matter of who takes which 32 frames.
 template <bool kB>
-__global__ void __launch_bounds__(kKfThreads, kB ? 5 : 8)
+__global__ void __launch_bounds__(kKfThreads, kB ? 6 : 8)
 kf_frames(const ChunkArgs a, const uint32_t nseg)
 {
     extern __shared__ __align__(256) uint8_t smem[];
@@ -676,7 +683,7 @@ kf_frames(const ChunkArgs a, const uint32_t nseg)
     uint32_t *const cnt = a.kf_count;
     const uint32_t *const bound = cnt + kSegBound + l * (kMaxSeg + 1);
     uint32_t *const next = cnt + kSegNext + l * kMaxSeg;
-    uint8_t *wsm = smem + (threadIdx.x >> 5) * (kB ? kKfWarpSmemB : kKfWarpSmemA);
+    uint8_t *wsm = smem + (threadIdx.x >> 5) * (kB ? kKfWarpSmemA + 32u * kf_aring_stride(a.kf_row, a.ns) : kKfWarpSmemA);
     uint32_t seg = 0;
     if (lane == 0) {                                      // the segment of this SM: the first warp to arrive claims one
         uint32_t smid;
@@ -793,11 +800,11 @@ cudaError_t launch_kf_sort(const ChunkArgs &a, cudaStream_t st, uint32_t *launch
 // The frame-lane kernels live on shared memory (three lane-private rings per lane) and barely use L1: ask for
 // the largest shared-memory carve-out so that the register file, not the carve-out, bounds the blocks per SM.
 template <bool kB>
-static cudaError_t kf_attributes(int *blocks_per_sm, int *smem_bytes)
+static cudaError_t kf_attributes(const ChunkArgs &a, int *blocks_per_sm, int *smem_bytes)
 {
     // ALACGPU_KF_PAD_A / _B (KB): extra dynamic shared memory per block, i.e. fewer resident blocks per SM (tuning runs)
     static const int pad = getenv(kB ? "ALACGPU_KF_PAD_B" : "ALACGPU_KF_PAD_A") ? atoi(getenv(kB ? "ALACGPU_KF_PAD_B" : "ALACGPU_KF_PAD_A")) * 1024 : 0;
-    const int smem = 2 * (int)(kB ? kKfWarpSmemB : kKfWarpSmemA) + pad;
+    const int smem = 2 * (int)(kB ? kKfWarpSmemA + 32u * kf_aring_stride(a.kf_row, a.ns) : kKfWarpSmemA) + pad;
     if (cudaError_t e = cudaFuncSetAttribute(kf_frames<kB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) return e;
     if (cudaError_t e = cudaFuncSetAttribute(kf_frames<kB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return e;
     int nb = 0;
@@ -818,7 +825,7 @@ cudaError_t launch_kf_a(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
     int per_sm = 1, smem = 0;
-    if (cudaError_t e = kf_attributes<false>(&per_sm, &smem)) return e;
+    if (cudaError_t e = kf_attributes<false>(a, &per_sm, &smem)) return e;
     const uint32_t nseg = kf_segments();
     // persistent warps: as many blocks as fit the machine at once (fewer for a chunk that cannot fill it)
     const uint32_t blocks = std::min<uint32_t>(nseg * (uint32_t)per_sm, a.kf_cap / kKfThreads);
@@ -831,7 +838,7 @@ cudaError_t launch_kf_b(const ChunkArgs &a, cudaStream_t st, uint32_t *launches)
 {
     if (a.n == 0) return cudaSuccess;
     int per_sm = 1, smem = 0;
-    if (cudaError_t e = kf_attributes<true>(&per_sm, &smem)) return e;
+    if (cudaError_t e = kf_attributes<true>(a, &per_sm, &smem)) return e;
     const uint32_t nseg = kf_segments();
     const uint32_t blocks = std::min<uint32_t>(nseg * (uint32_t)per_sm, a.kf_cap / kKfThreads);
     kf_frames<true><<<blocks, kKfThreads, smem, st>>>(a, nseg);

@@ -81,6 +81,18 @@ struct DevBuf {
         cap = want;
         return cudaSuccess;
     }
+    // exactly n elements (the multi-gigabyte planes of the frame-lane path: no growth slack)
+    cudaError_t reserve_exact(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = n;
+        return cudaSuccess;
+    }
     // grow, keeping the first `keep` elements (the arena of a context whose earlier tracks stay resident)
     cudaError_t reserve_keep(size_t n, size_t keep)
     {
@@ -682,6 +694,7 @@ uint32_t chunk_frames_for(const alacgpu_ctx *ctx, const Device &d, bool stage)
     if (!cf) {
         if (stage) {
             cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
+            if (kf) cf = (uint32_t)std::min<uint64_t>(cf, std::max<uint64_t>(32768, plane_budget(d) / 2 / d.kf_row));
         } else if (kf) {
             // the whole shard in one chunk if its plane fits, else as few chunks as two alternating slots allow
             const uint64_t budget = std::max<uint64_t>(plane_budget(d), 2ull * 32768 * d.kf_row);
@@ -716,13 +729,31 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
     const size_t n_chunks = d.chunks.size();
     // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
     d.slots_n = kSlots;
-    if (d.frame_lanes)
-        d.slots_n = (int)std::max<uint64_t>(2, std::min<uint64_t>(kSlots, plane_budget(d) / std::max<uint64_t>(1, (uint64_t)cf * d.kf_row)));
+    const size_t kf_plane_elems = ((size_t)cf * d.kf_row + 3u) / 4u + 64u;
+    if (d.frame_lanes) {
+        // As many slots as HBM has room for: two when the inputs are resident (the persistent kernels of
+        // consecutive chunks run one after the other anyway), four while chunks stream in.  A slot whose plane is
+        // already big enough costs nothing; growing one frees its old buffer first.
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        int64_t room = (int64_t)free_b - (int64_t)(2ull << 30);
+        int fit = 0;
+        for (int s = 0; s < (stage ? 4 : 2); s++) {
+            const size_t have = d.slots[s].planes.cap;
+            if (have < kf_plane_elems) {
+                const int64_t cost = (int64_t)(kf_plane_elems - have) * (int64_t)sizeof(int32_t);
+                if (room < cost) break;
+                room -= cost;
+            }
+            fit++;
+        }
+        d.slots_n = std::max(1, fit);
+    }
     const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
     if (decode)
         for (int s = 0; s < slots_used; s++) {
             if (d.frame_lanes) {
-                CUD(d.slots[s].planes.reserve(((size_t)cf * d.kf_row + 3u) / 4u + 64u));          // one row per frame (channel A)
+                CUD(d.slots[s].planes.reserve_exact(kf_plane_elems));          // one row per frame (channel A)
                 CUD(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
             } else {
                 CUD(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
