@@ -475,6 +475,31 @@ def latency_leg(name, args, local):
             "parity": "bit-exact vs the encoder's input + device checksum"}
 
 
+def copy_ceiling(torch, device, barrier, nbytes=1 << 30, reps=4):
+    """What the host can move for this rank while every other rank does the same: one H2D and one D2H stream of
+    page-locked 1 GiB copies running at the same time (the shape of the end-to-end pipeline), GB/s each way.
+    Under N ranks all of them measure between the same barriers, so the sum is the box's ceiling at N."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    d_out = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def go(n):
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+    go(1)
+    barrier()
+    t0 = time.perf_counter()
+    go(reps)
+    barrier()
+    dt = time.perf_counter() - t0
+    return nbytes * reps / dt / 1e9
+
+
 def load_profile_json(name):
     try:
         with open(os.path.join(ROOT, "profiles", name)) as f:
@@ -590,6 +615,7 @@ def run_ours(args):
         if not ok_e:
             raise SystemExit(f"bench.py: rank {rank}: end-to-end PCM differs from the encoder's input")
         e2e = {"ms": ms, "groups": ngroups, "tm": tm_e2e, "cap": cap}
+    ceiling = copy_ceiling(torch, torch.device("cuda", devices[0]), barrier) if (e2e and not single) else None
     e2e_pg = None
     if args.e2e_pageable_steps > 0:
         avail = mem_available()
@@ -606,7 +632,7 @@ def run_ours(args):
     # ---- max over ranks ---------------------------------------------------------------------------------
     vec = torch.tensor([dev_ms, wall_ms, e2e["ms"] if e2e else 0.0, e2e_pg["ms"] if e2e_pg else 0.0],
                        dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(samples), float(launches), float(n_frames), float(pcm_bytes), float(comp_bytes)],
+    tot = torch.tensor([float(samples), float(launches), float(n_frames), float(pcm_bytes), float(comp_bytes), float(ceiling or 0.0)],
                        dtype=torch.float64, device="cuda")
     ranges = torch.zeros(world * 2, dtype=torch.float64, device="cuda")
     # this rank's global frame range (for the line's evidence that the shards differ)
@@ -617,7 +643,7 @@ def run_ours(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(ranges, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_ms_max, e2e_ms_max, e2e_pg_ms_max = (float(x) for x in vec.tolist())
-    samples_all, launches_all, frames_all, pcm_all, comp_all = (float(x) for x in tot.tolist())
+    samples_all, launches_all, frames_all, pcm_all, comp_all, ceiling_all = (float(x) for x in tot.tolist())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -688,6 +714,9 @@ def run_ours(args):
                            "h2d_bytes_per_step": int(comp_all + 4 * frames_all), "d2h_bytes_per_step": int(pcm_all),   # whole job
                            "ms_per_step": e2e_ms_max, "steps": args.e2e_steps, "decode_all_calls_per_step": e2e["groups"],
                            "host_buffers": "page-locked (alacgpu_host_alloc)", "host_out_buffer_bytes": e2e["cap"],
+                           "achieved_copy_gbs_each_way": (comp_all + pcm_all) / 2 / (e2e_ms_max * 1e-3) / 1e9,
+                           "host_copy_ceiling_gbs_each_way": ceiling_all or None,
+                           "host_copy_ceiling_note": "sum over ranks of simultaneous page-locked 1 GiB H2D + D2H copies, all ranks between the same barriers",
                            "last_call": {k: tm_e[k] for k in ("h2d_ms", "d2h_ms", "kernels_ms", "total_ms")}}
         if e2e_pg:
             line["e2e_pageable"] = {"value": samples_all / (e2e_pg_ms_max * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_pg_ms_max,
