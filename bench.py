@@ -83,6 +83,9 @@ class Corpus:
 
 
 def make_corpus(name: str, world: int, args) -> Corpus:
+    # torchrun exports OMP_NUM_THREADS=1; the synthetic encoder (OpenMP over frames) should use this rank's share of the host
+    ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_cores() // max(1, ranks_here)))
     from tools.alacgen import alacgen as g
     g.build_encoder()
     s = args.scale
@@ -589,8 +592,12 @@ def run_ours(args):
     acc = {"index_ms": 0.0, "entropy_ms": 0.0, "lpc_ms": 0.0, "stereo_ms": 0.0, "kernels_ms": 0.0}
     launches = 0
     chunks = 0
+    step_ms, api_ms = [], []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         tm = step()
+        step_ms.append((time.perf_counter() - ts) * 1e3)
+        api_ms.append(tm["total_ms"])
         for k in acc:
             acc[k] += tm[k]
         launches += tm["kernel_launches"]
@@ -693,6 +700,7 @@ def run_ours(args):
                 "setup_s": t_setup, "numa_bind": numa, "chunks_per_step": chunks,
             },
             "device_ms_per_step": dev_ms_max,
+            "step_wall_ms_rank0": [round(x, 2) for x in step_ms], "decode_all_ms_rank0": [round(x, 2) for x in api_ms],
             "stage_ms": stage,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
