@@ -327,12 +327,12 @@ struct PlaneRing {
 };
 
 // ---- one entropy step with the residual left in a register ------------------------------------------
-// k1_entropy.cuh's ALACGPU_ENTROPY_STEP with three changes: a lane that still holds an unconsumed
-// residual (%15 have) or owes zeros of a run (%14 pend) sits the step out; a completed value goes to %16 instead of a plane; a completed
+// k1_entropy.cuh's ALACGPU_ENTROPY_STEP with three changes: a lane that still holds unconsumed residuals
+// (%14 cnt: 1 after a value, r after a run of r zeros) sits the step out; a completed value goes to %15 instead of a plane; a completed
 // zero-run length becomes %14 = the number of zero residuals still to hand out (clipped to the frame)
 // while the symbol index jumps as before.  Operands:
 //   %0 cur %1 nxt %2 nn %3 off %4 wpos | %5 i %6 nc %7 h %8 smm1 %9 kk %10 mk %11 mm %12 R %13 W
-//   %14 pend %15 have %16 e | %17 ring %18 mult %19 rssh %20 kcap %21 kmask %22 kk after a run
+//   %14 cnt %15 e | %16 ring %17 mult %18 rssh %19 kcap %20 kmask %21 kk after a run
 #define ALACGPU_ENTROPY_STEP_F                                                                            \
     "setp.ne.u32 pR, %12, 0;\n\t"                                                                         \
     "setp.ne.u32 pW, %13, 0;\n\t"                                                                         \
@@ -352,14 +352,13 @@ struct PlaneRing {
     "setp.ge.u32 pbig, ee, 2;\n\t"                                                                        \
     "mad.lo.u32 rice, x, %11, %8;\n\t"                                                                    \
     "add.u32 rice, rice, em;\n\t"                                                                         \
-    "selp.u32 rsh, 16, %19, pR;\n\t"                                                                      \
+    "selp.u32 rsh, 16, %18, pR;\n\t"                                                                      \
     "shr.u32 rawv, w, rsh;\n\t"                                                                           \
     "add.u32 rawv, rawv, %8;\n\t"                                                                         \
     "add.u32 rawv, rawv, 1;\n\t"                                                                          \
     "selp.u32 dv, rawv, rice, pW;\n\t"                                                                    \
     "setp.lt.u32 pA, %5, %6;\n\t"                                                                         \
-    "setp.eq.and.u32 pA, %15, 0, pA;\n\t"              /* a lane with a residual in hand waits, */        \
-    "setp.eq.and.u32 pA, %14, 0, pA;\n\t"              /* and so does one that still owes zeros of a run */ \
+    "setp.eq.and.u32 pA, %14, 0, pA;\n\t"              /* a lane with residuals in hand (a value, or zeros of a run) waits */ \
     "not.pred nA, pA;\n\t"                                                                                \
     "sub.u32 alt, 32, rsh;\n\t"                                                                           \
     "selp.u32 alt, alt, 9, pW;\n\t"                                                                       \
@@ -377,7 +376,7 @@ struct PlaneRing {
     "prmt.b32 %1, %2, %1, sel;\n\t"                                                                       \
     "and.b32 wa, %4, 63;\n\t"                                                                             \
     "shl.b32 wa, wa, 2;\n\t"                                                                              \
-    "add.u32 wa, wa, %17;\n\t"                                                                            \
+    "add.u32 wa, wa, %16;\n\t"                                                                            \
     "@prf ld.shared.u32 %2, [wa];\n\t"                                                                    \
     "@prf add.u32 %4, %4, 1;\n\t"                                                                         \
     "not.pred nW, pW;\n\t"                                                                                \
@@ -392,12 +391,12 @@ struct PlaneRing {
     "neg.s32 t1, t1;\n\t"                                                                                 \
     "shr.u32 t2, dv, 1;\n\t"                                                                              \
     "xor.b32 t2, t2, t1;\n\t"                                                                             \
-    "@pV mov.b32 %16, t2;\n\t"                         /* the residual (:225-226) */                      \
-    "@pV mov.u32 %15, 1;\n\t"                                                                             \
-    "mul.lo.u32 t3, %7, %18;\n\t"                                                                         \
+    "@pV mov.b32 %15, t2;\n\t"                         /* the residual (:225-226) */                      \
+    "@pV mov.u32 %14, 1;\n\t"                                                                             \
+    "mul.lo.u32 t3, %7, %17;\n\t"                                                                         \
     "shr.s32 t3, t3, 9;\n\t"                                                                              \
     "sub.s32 t3, %7, t3;\n\t"                                                                             \
-    "mad.lo.u32 hn, dv, %18, t3;\n\t"                                                                     \
+    "mad.lo.u32 hn, dv, %17, t3;\n\t"                                                                     \
     "setp.gt.u32 pbv, dv, 0xFFFF;\n\t"                                                                    \
     "selp.s32 hn, 0xFFFF, hn, pbv;\n\t"                                                                   \
     "add.u32 isum, %5, dv;\n\t"                                                                           \
@@ -419,7 +418,7 @@ struct PlaneRing {
     "add.s32 fk, t5, 0x4B000003;\n\t"                                                                     \
     "add.rn.f32 fk, fk, 0fCB000000;\n\t"                                                                  \
     "shr.b32 t5, fk, 23;\n\t"                                                                             \
-    "min.u32 kkv, t5, %20;\n\t"                                                                           \
+    "min.u32 kkv, t5, %19;\n\t"                                                                           \
     "bfind.u32 t6, hn;\n\t"                                                                               \
     "add.u32 t7, hn, 16;\n\t"                                                                             \
     "shr.u32 t7, t7, 6;\n\t"                                                                              \
@@ -427,13 +426,13 @@ struct PlaneRing {
     "add.u32 t7, t7, 134;\n\t"                                                                            \
     "setp.eq.u32 pz, hn, 0;\n\t"                                                                          \
     "selp.u32 t7, 143, t7, pz;\n\t"                                                                       \
-    "selp.u32 kn, %22, kkv, pU;\n\t"                                                                       \
+    "selp.u32 kn, %21, kkv, pU;\n\t"                                                                       \
     "selp.u32 kn, t7, kn, pT;\n\t"                                                                         \
     "and.pred pC, pA, nP;\n\t"                         /* a symbol was completed: only then k moves on */  \
     "@pC mov.u32 %9, kn;\n\t"                                                                             \
     "shf.l.wrap.b32 t8, 2, 2, %9;\n\t"                                                                    \
     "sub.u32 %10, t8, 1;\n\t"                                                                             \
-    "selp.u32 t9, %21, 0xFFFFFFFF, pT;\n\t"                                                               \
+    "selp.u32 t9, %20, 0xFFFFFFFF, pT;\n\t"                                                               \
     "and.b32 t9, %10, t9;\n\t"                                                                            \
     "@pC mov.u32 %11, t9;\n\t"                                                                            \
     "and.pred q0, pP, pR;\n\t"                                                                            \
@@ -545,7 +544,7 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
     uint32_t i = 0, nc = n;
     int32_t h = h0;
     uint32_t smm1 = 0xFFFFFFFFu, kk = kk0, mk = (1u << (kk0 - 127u)) - 1u, mm = mk, R = 0, W = 0;
-    uint32_t pend = 0, have = 0;
+    uint32_t cnt = 0;                                                // residuals in hand: `e`, then zeros
     int32_t e = 0;
 
     LaneLpc<M> lpc;
@@ -591,8 +590,8 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
         cp_async_commit();
         cp_async_wait<1>();
         out.flush<7>();
-        if (!__any_sync(0xffffffffu, have != 0u || pend != 0u || i < nc)) break;
-        if (period >= max_periods) { stuck = have != 0u || pend != 0u || i < nc; break; }
+        if (!__any_sync(0xffffffffu, cnt != 0u || i < nc)) break;
+        if (period >= max_periods) { stuck = cnt != 0u || i < nc; break; }
 #pragma unroll 1
         for (int u = 0; u < kKfPeriod; ++u) {
             asm volatile(
@@ -603,13 +602,13 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
                 ALACGPU_ENTROPY_STEP_F
                 "}"
                 : "+r"(br.cur), "+r"(br.nxt), "+r"(br.nn), "+r"(br.off), "+r"(br.wpos), "+r"(i), "+r"(nc), "+r"(h),
-                  "+r"(smm1), "+r"(kk), "+r"(mk), "+r"(mm), "+r"(R), "+r"(W), "+r"(pend), "+r"(have), "+r"(e)
+                  "+r"(smm1), "+r"(kk), "+r"(mk), "+r"(mm), "+r"(R), "+r"(W), "+r"(cnt), "+r"(e)
                 : "r"(br.ring), "r"(mult), "r"(rssh), "r"(kcap), "r"(kmask), "r"(kk_after_run)
                 : "memory");
-            if (have == 0u && pend != 0u) { have = 1u; e = 0; --pend; }      // a zero of the current run (:238-245)
             // the predictor runs when every lane that is still decoding has a residual in hand
-            if (__all_sync(0xffffffffu, have != 0u || i >= nc)) {
-                const bool hv = have != 0u;
+            if (__all_sync(0xffffffffu, cnt != 0u || i >= nc)) {
+                const uint32_t have = min(cnt, 1u);                   // 0 / 1: this lane has a sample this round
+                const bool hv = cnt != 0u;
                 const int32_t o = lpc.step(e, j, hv);
                 if (to_plane) {
                     if (is24_w) out.put32((uint32_t)o, have); else out.put16((uint32_t)o, have);
@@ -645,7 +644,8 @@ __device__ __noinline__ void kf_run(const ChunkArgs &a, const uint32_t slot_in, 
                     }
                 }
                 j += hv ? 1u : 0u;
-                have = 0u;
+                cnt -= have;
+                e = 0;                                                // what is left in hand are zeros of a run (:238-245)
             }
         }
     }
