@@ -20,7 +20,39 @@
 
 #include <cuda_runtime.h>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define ALACGPU_HAVE_STREAM_STORES 1
+#endif
+
 namespace alacgpu {
+
+// dst[0, n) = src[0, n) with non-temporal stores: the PCM that leaves a ring slot for the caller's buffer is not
+// read again soon, and an ordinary store would first pull every destination line into the cache (the end-to-end
+// path from / to pageable memory is bound by host DRAM traffic: every byte crosses it three to four times).
+inline void copy_streaming(uint8_t *dst, const uint8_t *src, uint64_t n)
+{
+#ifdef ALACGPU_HAVE_STREAM_STORES
+    uint64_t head = (16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (head > n) head = n;
+    if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    const uint64_t body = n & ~(uint64_t)63;
+    for (uint64_t i = 0; i < body; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+    }
+    _mm_sfence();
+    if (n > body) memcpy(dst + body, src + body, n - body);
+#else
+    memcpy(dst, src, n);
+#endif
+}
 
 // A few host threads that copy memory in parallel (one memcpy per thread saturates one core's load/store
 // bandwidth, ~10 GB/s; PCIe Gen5 moves ~55 GB/s each way).
@@ -40,11 +72,12 @@ public:
         for (std::thread &t : workers_) t.join();
     }
     int threads() const { return (int)workers_.size(); }
-    // dst[0, len) = src[0, len), split over the pool; returns when every part is done
-    void copy(uint8_t *dst, const uint8_t *src, uint64_t len)
+    // dst[0, len) = src[0, len), split over the pool; returns when every part is done.  `streaming`: the
+    // destination is written with non-temporal stores (copy_streaming)
+    void copy(uint8_t *dst, const uint8_t *src, uint64_t len, bool streaming = false)
     {
         const int parts = (int)std::min<uint64_t>((uint64_t)workers_.size(), (len + kMinPart - 1) / kMinPart);
-        if (parts <= 1) { memcpy(dst, src, len); return; }
+        if (parts <= 1) { if (streaming) copy_streaming(dst, src, len); else memcpy(dst, src, len); return; }
         std::atomic<int> left{parts};
         std::mutex dm;
         std::condition_variable dcv;
@@ -54,7 +87,7 @@ public:
             for (int p = 0; p < parts; p++) {
                 const uint64_t lo = std::min<uint64_t>(len, step * p), hi = std::min<uint64_t>(len, step * (p + 1));
                 q_.push_back([=, &left, &dm, &dcv] {
-                    if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
+                    if (hi > lo) { if (streaming) copy_streaming(dst + lo, src + lo, hi - lo); else memcpy(dst + lo, src + lo, hi - lo); }
                     if (left.fetch_sub(1) == 1) {
                         std::lock_guard<std::mutex> g2(dm);
                         dcv.notify_one();

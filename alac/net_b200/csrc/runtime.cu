@@ -172,6 +172,11 @@ struct Device {
     bool chunk_taper = false;
     PinnedRing ring_in, ring_out;     // page-locked staging for pageable callers (host_staging.h)
     std::unique_ptr<Progress> h2d_prog, k_prog;   // stager -> issuer -> drainer hand-over of recorded events
+    // chunk size and slot count of the frame-lane path per mode ([0] resident inputs, [1] streamed in), decided once
+    // per plan: the decision asks the driver for free memory (cudaMemGetInfo), which was seen to take 30-100 ms
+    // now and then -- not something to do in every decode_all
+    mutable uint32_t cf_cache[2] = {0, 0};
+    int slots_cache[2] = {0, 0};
     bool frame_lanes = false;         // this pipeline run decodes with the frame-lane kernels
     int slots_n = kSlots;             // slot streams in use by this pipeline run
     std::vector<cudaEvent_t> events;
@@ -291,7 +296,10 @@ void invalidate(alacgpu_ctx *ctx)
     ctx->planned = false;
     ctx->have_status = false;
     ctx->win_lo = ctx->win_hi = 0;
-    for (Device &d : ctx->devs) { d.resident = false; d.decoded = false; d.pcm_resident = false; d.chunk_frames = 0; d.chunks.clear(); }
+    for (Device &d : ctx->devs) {
+        d.resident = false; d.decoded = false; d.pcm_resident = false; d.chunk_frames = 0; d.chunks.clear();
+        d.cf_cache[0] = d.cf_cache[1] = 0; d.slots_cache[0] = d.slots_cache[1] = 0;
+    }
 }
 
 // Is `p` page-locked (cudaHostAlloc / cudaHostRegister / alacgpu_host_alloc) memory?
@@ -331,6 +339,7 @@ int32_t build_plan(alacgpu_ctx *ctx)
         d.resident = d.decoded = d.pcm_resident = false;
         d.chunks.clear();
         d.chunk_frames = 0;
+        d.cf_cache[0] = d.cf_cache[1] = 0; d.slots_cache[0] = d.slots_cache[1] = 0;
         const uint64_t n_local = d.f_hi - d.f_lo;
         CU(cudaSetDevice(d.id));
         d.h_refs.assign(n_local, FrameRef{});
@@ -691,6 +700,7 @@ uint32_t chunk_frames_for(const alacgpu_ctx *ctx, const Device &d, bool stage)
     const bool kf = frame_lanes_for(ctx, d);
     const uint32_t cap = kf ? kFrameLaneMaxChunk : kMaxChunkFrames;
     uint32_t cf = ctx->opts.chunk_frames;
+    if (!cf && kf && d.cf_cache[stage ? 1 : 0]) return d.cf_cache[stage ? 1 : 0];
     if (!cf) {
         if (stage) {
             cf = (uint32_t)std::max<uint64_t>(kf ? 32768 : 256, (n_local + kSlots - 1) / kSlots);
@@ -704,6 +714,9 @@ uint32_t chunk_frames_for(const alacgpu_ctx *ctx, const Device &d, bool stage)
         } else {
             cf = (uint32_t)std::min<uint64_t>(n_local, cap);
         }
+        cf = std::min<uint32_t>((cf + 31u) & ~31u, cap);
+        if (kf) d.cf_cache[stage ? 1 : 0] = cf;
+        return cf;
     }
     return std::min<uint32_t>((cf + 31u) & ~31u, cap);
 }
@@ -730,7 +743,9 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
     // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
     d.slots_n = kSlots;
     const size_t kf_plane_elems = ((size_t)cf * d.kf_row + 3u) / 4u + 64u;
-    if (d.frame_lanes) {
+    if (d.frame_lanes && d.slots_cache[stage ? 1 : 0] && !ctx->opts.chunk_frames) {
+        d.slots_n = d.slots_cache[stage ? 1 : 0];
+    } else if (d.frame_lanes) {
         // As many slots as HBM has room for: two when the inputs are resident (the persistent kernels of
         // consecutive chunks run one after the other anyway), four while chunks stream in.  A slot whose plane is
         // already big enough costs nothing; growing one frees its old buffer first.
@@ -748,6 +763,7 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
             fit++;
         }
         d.slots_n = std::max(1, fit);
+        d.slots_cache[stage ? 1 : 0] = d.slots_n;
     }
     const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
     if (decode)
@@ -830,7 +846,7 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
         const Flying f = flying.front();
         flying.pop_front();
         CUD(cudaEventSynchronize(d.ring_out.ev[f.slot]));
-        ctx->pool->copy(f.dst, d.ring_out.buf[f.slot], f.len);
+        ctx->pool->copy(f.dst, d.ring_out.buf[f.slot], f.len, /*streaming=*/true);
         d.ring_out.busy[f.slot] = false;
         return true;
     };

@@ -22,7 +22,7 @@ static int check_copy_pool()
         for (uint64_t i = 0; i < src.size(); i++) src[i] = (uint8_t)(rng() >> 13);
         const uint64_t so = rng() % 64, doff = rng() % 64;
         const uint64_t n = len > std::max(so, doff) ? len - std::max(so, doff) : 0;
-        pool.copy(dst.data() + doff, src.data() + so, n);
+        pool.copy(dst.data() + doff, src.data() + so, n, /*streaming=*/(round & 1) != 0);
         for (uint64_t i = 0; i < n; i++)
             if (dst[doff + i] != src[so + i]) { printf("copy mismatch at %llu of %llu\n", (unsigned long long)i, (unsigned long long)n); return 1; }
         for (uint64_t i = 0; i < doff; i++) if (dst[i] != 0xEE) { printf("wrote before the destination\n"); return 1; }
