@@ -267,3 +267,43 @@ def test_iso_demux_survives_crafted_sizes(built, gen):
     plain[s + 4:s + 12] = struct.pack(">II", 4096, 0xFFFFFFFF)
     d = H.iso_demux(bytes(plain))
     assert d["stsz"].size <= len(plain) // 4096 + 1
+
+
+def test_bench_checksum_bookkeeping(gen):
+    """bench.py checks a batch of physically replicated tracks against the encoder's input without touching every
+    replica: the position-weighted checksum of a track placed at 8-byte word `first` is S1 + 2 first S0 (S0 = sum of
+    words, S1 = the checksum at position 0).  Pieces cut by a shard boundary are summed directly."""
+    import types
+    import bench
+    from alac.net_b200 import host_checksum
+    args = types.SimpleNamespace(scale=0.004, tracks=7, unique=3, tracks_per_gpu=0, unique_per_kind=1, orders="0,31")
+    corpus = bench.make_corpus("config4", 1, args)
+    assert corpus.n_tracks == 7 and len(corpus.uniq) == 3
+    pieces = bench.rank_pieces(corpus, 1, 0)
+    # lay the tracks out like the decoder does (256-byte aligned starts) and compare with the formula
+    off, layout = 0, []
+    for p in pieces:
+        off = (off + 255) // 256 * 256
+        layout.append((off, p.p_hi - p.p_lo))
+        off += p.p_hi - p.p_lo
+    buf = np.zeros(off, dtype=np.uint8)
+    for p, (o, l) in zip(pieces, layout):
+        buf[o:o + l] = np.frombuffer(corpus.uniq[p.u].pcm, dtype=np.uint8)[p.p_lo:p.p_hi]
+
+    class FakeDecoder:
+        def track_pcm_bytes(self, i):
+            return layout[i]
+    assert bench.expected_checksum(corpus, FakeDecoder(), pieces) == host_checksum(buf)
+    # a sharded run: the pieces of both ranks cover every frame once, and partial pieces take the direct sum
+    args5 = types.SimpleNamespace(scale=0.004, tracks=20, unique=3, tracks_per_gpu=10, unique_per_kind=1, orders="0,31")
+    c5 = bench.make_corpus("config5", 2, args5)
+    got = {}
+    for rank in range(2):
+        for p in bench.rank_pieces(c5, 2, rank):
+            got.setdefault(p.j, []).append((p.f_lo, p.f_hi))
+    for j in range(c5.n_tracks):
+        spans = sorted(got[j])
+        assert spans[0][0] == 0 and spans[-1][1] == c5.track(j).n_frames
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    groups = bench.groups_for(bench.rank_pieces(c5, 2, 0), 1 << 20)
+    assert sum(len(g) for g in groups) == len(bench.rank_pieces(c5, 2, 0)) and len(groups) > 1
