@@ -51,10 +51,10 @@ constexpr int kSlots = 16;
 constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
 // Frame-lane path (kf_frame.cu): one lane per frame and channel from bitstream to PCM.  A lane's task is 32
 // frames x 4096 samples (~5 ms), so the path needs MANY tasks per SM before its tails stop mattering: measured
-// on B200 (16-bit stereo, resident inputs) 46.6 vs 62.9 Gsamples/s for the stream-lane kernels at 174 k frames,
-// 53 vs 66 at 678 k, 68.3 vs 66.4 at 2.71 M -- with 1.6x instead of 4.2x the algorithmic bytes in DRAM traffic.
-// A device whose share of the batch holds at least this many frames takes it.
-constexpr uint64_t kFrameLaneMinFrames = 1500000;
+// on B200 (16-bit stereo, resident inputs) 46.6 vs 62.9 Gsamples/s for the stream-lane kernels at 174 k frames
+// (an earlier r2 build), 66.1 vs 66.1 at 678 k, 77.6 vs 66.4 at 2.71 M -- with 1.7x instead of 4.2x the
+// algorithmic bytes in DRAM traffic.  A device whose share of the batch holds at least this many frames takes it.
+constexpr uint64_t kFrameLaneMinFrames = 650000;
 constexpr uint32_t kFrameLaneMaxChunk = 8u << 20;
 // bytes of channel-A planes over all slots in flight.  Resident inputs: one chunk as big as this allows (a frame
 // lane's task is 32 frames x 4096 samples, ~5 ms: the fewer launches, the less of the machine idles in their

@@ -656,7 +656,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         stage = {k: acc[k] / args.steps for k in acc}
         b_alg = comp_bytes + pcm_bytes
-        frame_lanes = (not (args.flags & 0x42)) and ((args.flags & 0x80) or n_frames // max(1, len(devices)) >= int(os.environ.get("ALACGPU_KF_MIN", 1500000)))
+        frame_lanes = (not (args.flags & 0x42)) and ((args.flags & 0x80) or n_frames // max(1, len(devices)) >= int(os.environ.get("ALACGPU_KF_MIN", 650000)))
         fused = not (args.flags & 2)
         if frame_lanes:
             dom_name, dom_sum = "kf_frames", stage["entropy_ms"] + stage["lpc_ms"]

@@ -98,7 +98,7 @@ typedef struct alacgpu_ctx alacgpu_ctx;
  * lanes): one fused entropy + LPC launch per chunk (LPC warps consume residuals while the entropy lanes still
  * produce them) followed by the un-mix / pack kernel; when the inputs are resident and pcm_dst is page-locked,
  * ONE launch with entropy, LPC and pack roles that writes the PCM straight into the destination (no device
- * PCM, no D2H stage).  Big batches (>= 1.5 M frames per device): the frame-lane kernels -- one lane per frame
+ * PCM, no D2H stage).  Big batches (>= 650 k frames per device): the frame-lane kernels -- one lane per frame
  * and channel from bitstream to PCM, no residual / sample planes in HBM except a half-width copy of channel A
  * of stereo frames. */
 #define ALACGPU_FLAG_KEEP_DEVICE_PCM 0x1u    /* keep decoded PCM resident in HBM after decode_all */

@@ -93,7 +93,7 @@ def test_random_payload_fuzz(seed, gen, oracle):
 
 
 def test_default_policy_takes_the_frame_lanes_for_a_big_batch(gen, monkeypatch):
-    """At or above the frame threshold (1.5 M frames per device; lowered here through ALACGPU_KF_MIN so that the
+    """At or above the frame threshold (650 k frames per device; lowered here through ALACGPU_KF_MIN so that the
     test stays small) no flag is needed.  70,000 frames of 256 samples (16-bit stereo and the
     16/24-bit mono/stereo mix), checked against the encoder's input and by the device checksum; the same batch
     through the stream-lane kernels (ALACGPU_FLAG_NO_FRAME_LANES) gives the same bytes."""
