@@ -59,7 +59,7 @@ constexpr uint32_t kFrameLaneMaxChunk = 8u << 20;
 // bytes of channel-A planes over all slots in flight.  Resident inputs: one chunk as big as this allows (a frame
 // lane's task is 32 frames x 4096 samples, ~5 ms: the fewer launches, the less of the machine idles in their
 // tails); inputs streamed in: chunks of 1/16 of the frames, as many slots as fit
-constexpr uint64_t kFrameLanePlaneBudget = 48ull << 30;
+constexpr uint64_t kFrameLanePlaneBudget = 96ull << 30;
 constexpr uint64_t kReadWindow = 8ull << 20;   // host-side cache window of alacgpu_read_frame
 constexpr uint64_t kRingSlotBytes = 16ull << 20;   // one slot of the page-locked staging rings (host_staging.h)
 
@@ -735,48 +735,62 @@ bool run_device(alacgpu_ctx *ctx, Device &d, const PipeArgs &pa, DevRun &res)
     const bool stage = pa.stage, index = pa.index, decode = pa.decode;
     uint8_t *const pcm_dst = pa.pcm_dst;
     uint8_t *const zc = pa.zc;
-    const uint32_t cf = chunk_frames_for(ctx, d, stage);
     d.frame_lanes = frame_lanes_for(ctx, d);
     static const bool no_taper = getenv("ALACGPU_NO_TAPER") != nullptr;
-    build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper && !d.frame_lanes);
-    const size_t n_chunks = d.chunks.size();
-    // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
-    d.slots_n = kSlots;
-    const size_t kf_plane_elems = ((size_t)cf * d.kf_row + 3u) / 4u + 64u;
-    if (d.frame_lanes && d.slots_cache[stage ? 1 : 0] && !ctx->opts.chunk_frames) {
-        d.slots_n = d.slots_cache[stage ? 1 : 0];
-    } else if (d.frame_lanes) {
-        // As many slots as HBM has room for: two when the inputs are resident (the persistent kernels of
-        // consecutive chunks run one after the other anyway), four while chunks stream in.  A slot whose plane is
-        // already big enough costs nothing; growing one frees its old buffer first.
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
-        int64_t room = (int64_t)free_b - (int64_t)(2ull << 30);
-        int fit = 0;
-        for (int s = 0; s < (stage ? 4 : 2); s++) {
-            const size_t have = d.slots[s].planes.cap;
-            if (have < kf_plane_elems) {
-                const int64_t cost = (int64_t)(kf_plane_elems - have) * (int64_t)sizeof(int32_t);
-                if (room < cost) break;
-                room -= cost;
+    uint32_t cf = chunk_frames_for(ctx, d, stage);
+    size_t n_chunks = 0;
+    // Chunks, slots and their buffers.  The frame-lane planes are sized by what cudaMemGetInfo reports as free; if
+    // the allocation fails all the same (fragmentation, another tenant of the GPU), halve the chunk and try again
+    // rather than fail a decode that fits.
+    for (int attempt = 0;; attempt++) {
+        build_chunks(ctx, d, cf, stage && !ctx->opts.chunk_frames && !no_taper && !d.frame_lanes);
+        n_chunks = d.chunks.size();
+        // slots in flight: a frame-lane chunk fills the machine on its own, and its channel-A plane is big
+        d.slots_n = kSlots;
+        const size_t kf_plane_elems = ((size_t)cf * d.kf_row + 3u) / 4u + 64u;
+        if (d.frame_lanes && d.slots_cache[stage ? 1 : 0] && !ctx->opts.chunk_frames) {
+            d.slots_n = d.slots_cache[stage ? 1 : 0];
+        } else if (d.frame_lanes) {
+            // As many slots as HBM has room for: two when the inputs are resident (the persistent kernels of
+            // consecutive chunks run one after the other anyway), four while chunks stream in.  A slot whose plane is
+            // already big enough costs nothing; growing one frees its old buffer first.
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+            int64_t room = (int64_t)free_b - (int64_t)(2ull << 30);
+            int fit = 0;
+            for (int s = 0; s < (stage ? 4 : 2); s++) {
+                const size_t have = d.slots[s].planes.cap;
+                if (have < kf_plane_elems) {
+                    const int64_t cost = (int64_t)(kf_plane_elems - have) * (int64_t)sizeof(int32_t);
+                    if (room < cost) break;
+                    room -= cost;
+                }
+                fit++;
             }
-            fit++;
+            d.slots_n = std::max(1, fit);
+            d.slots_cache[stage ? 1 : 0] = d.slots_n;
         }
-        d.slots_n = std::max(1, fit);
-        d.slots_cache[stage ? 1 : 0] = d.slots_n;
+        const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
+        cudaError_t oom = cudaSuccess;
+        if (decode)
+            for (int s = 0; s < slots_used && oom == cudaSuccess; s++) {
+                if (d.frame_lanes) {
+                    oom = d.slots[s].planes.reserve_exact(kf_plane_elems);          // one row per frame (channel A)
+                    if (oom == cudaSuccess) CUD(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
+                } else {
+                    CUD(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
+                    CUD(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
+                    CUD(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
+                }
+            }
+        if (oom == cudaSuccess) break;
+        cudaGetLastError();
+        if (oom != cudaErrorMemoryAllocation || attempt >= 4 || cf <= 65536 || ctx->opts.chunk_frames) CUD(oom);
+        cf = ((cf / 2u) + 31u) & ~31u;
+        d.cf_cache[stage ? 1 : 0] = cf;
+        d.slots_cache[stage ? 1 : 0] = 0;
     }
     const int slots_used = (int)std::min<size_t>((size_t)d.slots_n, n_chunks);
-    if (decode)
-        for (int s = 0; s < slots_used; s++) {
-            if (d.frame_lanes) {
-                CUD(d.slots[s].planes.reserve_exact(kf_plane_elems));          // one row per frame (channel A)
-                CUD(d.slots[s].kf.reserve(kf_list_words(cf) + kKfCountWords + cf));
-            } else {
-                CUD(d.slots[s].planes.reserve((size_t)cf * 2u * d.ns));
-                CUD(d.slots[s].perm.reserve((size_t)cf * 4u + 1024u + 4u));
-                CUD(d.slots[s].progress.reserve((size_t)cf * 4u + 8u + ((size_t)cf * 2u + 3u) / 4u));
-            }
-        }
     const bool to_host = pcm_dst && !zc && decode;
     bool ring_in = false;
     if (stage)
