@@ -615,7 +615,7 @@ def run_ours(args):
     e2e = None
     if args.e2e_steps > 0:
         avail = mem_available()
-        cap = min(total + 4096, max(1 << 30, int(avail * 0.45) // (world if world > 1 else 1)))
+        cap = min(total + 4096, max(1 << 30, int(avail * 0.7) // (world if world > 1 else 1)))   # freed again before the pageable leg
         if args.e2e_buffer_gb > 0:
             cap = min(cap, int(args.e2e_buffer_gb * (1 << 30)))
         ms, ngroups, tm_e2e, ok_e = e2e_leg(dec, staged, pieces, args.e2e_steps, 2, barrier, True, cap)
@@ -626,7 +626,7 @@ def run_ours(args):
     e2e_pg = None
     if args.e2e_pageable_steps > 0:
         avail = mem_available()
-        cap = min(total + 4096, max(1 << 30, int(avail * 0.30) // (world if world > 1 else 1)))
+        cap = min(total + 4096, max(1 << 30, int(avail * 0.55) // (world if world > 1 else 1)))
         if args.e2e_buffer_gb > 0:
             cap = min(cap, int(args.e2e_buffer_gb * (1 << 30)))
         staged_pg = Staged(corpus, pinned=False)
