@@ -177,11 +177,12 @@ static cudaError_t clear_planes(const ChunkArgs &a, cudaStream_t st)
     return cudaMemsetAsync(a.planes, 0, (size_t)a.n * 2u * a.ns * sizeof(int32_t), st);
 }
 
-// upper bound of the four-lane warps (eight streams each); warps past the work lists exit at once
+// upper bound of the four-lane (eight-lane) warps, eight (four) streams each; warps past the work lists exit at once
 static uint32_t quad_warp_bound(const ChunkArgs &a)
 {
     const uint32_t per_frame = ((a.use_quads & 255) ? 1u : 0u) + ((a.use_quads >> 8) & 255 ? 1u : 0u);
-    return (a.n * per_frame + 7u) / 8u;
+    const uint32_t per_warp = ((a.use_quads >> 16) & 1) ? 4u : 8u;
+    return (a.n * per_frame + per_warp - 1u) / per_warp;
 }
 
 constexpr uint32_t kSmallChunkFrames = 20480;    // up to here a chunk is latency-bound (runtime.cu: kFullFusionMaxFrames)

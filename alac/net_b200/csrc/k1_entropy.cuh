@@ -186,7 +186,7 @@ constexpr uint32_t kStreamDone = 0xFFFFFFFFu;
 //   %0 cur  %1 nxt  %2 nn  %3 off  %4 wpos           bit cursor (BitCursor)
 //   %5 i    %6 nc   %7 h   %8 smm1 (signModifier-1)  output index, samples per channel, history
 //   %9 kk (k + 127)  %10 mk ((1<<k)-1)  %11 mm       parameters of the symbol at the cursor
-//   pR  pW (predicates, set by the code around the step)  kind of that symbol: run length / raw field
+//   %12 R  %13 W                                      kind of that symbol: run length / raw field (0|1)
 //   %14 ring  %15 mult  %16 rssh (32-rss)  %17 kcap (kmod+127)  %18 kmask  %19 kk after a run  %20 row
 // Predicates inside: pA lane active, pesc nine 1 bits, pP raw field pending, pV a value completed,
 // pU a run length completed, pT a run-length symbol is next.
@@ -296,136 +296,6 @@ constexpr uint32_t kStreamDone = 0xFFFFFFFFu;
     "or.pred pR, q0, q1;\n\t"                                                                             \
     "mov.pred pW, pP;\n\t"
 
-// ---- the common step ---------------------------------------------------------------------------------
-// Most steps of most warps find every lane in front of an ordinary value symbol.  A step therefore looks
-// first (ALACGPU_ENTROPY_LOOK: the window, its count of leading 1 bits, a warp vote) and goes on with
-// ALACGPU_ENTROPY_FAST when no lane is at a run-length symbol or a raw field: the arithmetic of the general step
-// without the kind selects, the run-length k and the two-step escape -- ~60 instead of ~90 instructions on
-// the frame's serial chain.  Four steps make one asm block laid out as
-//     look 1, fast 1, look 2, fast 2, look 3, fast 3, look 4, fast 4, bra END, G1: general 1, G2: general 2, ... END:
-// so the common path falls through not-taken branches; the first step of a group that needs the general path
-// jumps to its G label and the rest of the group runs there too.  Differences in state, undone by
-// ALACGPU_ENTROPY_PEND in front of every general step:
-//   * nine 1 bits followed by a raw field of at most 23 bits are decoded by the fast step, in one go (prefix and
-//     field fit the 32-bit window together: 16-bit material, 24-bit material with wasted bytes, :198-202);
-//     lanes with a wider raw field (%13 `exlim` = 1) send the warp down the general path for it;
-//   * when a value leaves a history below 128 (the next symbol is a run length, :231) or a negative one (the
-//     lane stops), the fast step only raises bit 2 of RW and keeps the history; PEND derives the run
-//     length's k from it (:234-236, clz(0) == 40) and clears it (:248), or stops the lane.
-// Operands: %0 cur %1 nxt %2 nn %3 off %4 wpos %5 i %6 nc %7 h %8 smm1 %9 kk %10 mk %11 mm
-//           %12 RW (bit 0 run length, bit 1 raw field, bit 2 run length pending) |
-//           %13 exlim %14 ring %15 mult %16 rssh %17 kcap %18 kmask %19 kk after a run %20 row %21 9 + rss
-#define ALACGPU_ENTROPY_LOOK(G)                                                                           \
-    "shf.l.wrap.b32 w, %1, %0, %3;\n\t"                                                                   \
-    "shr.u32 t0, w, 23;\n\t"                                                                              \
-    "lop3.b32 fx, t0, 0x1FF, 0x4B000000, 0xBE;\n\t"                                                       \
-    "add.rn.f32 fx, fx, 0fCB000000;\n\t"                                                                  \
-    "shr.b32 ex, fx, 23;\n\t"                                                                             \
-    "setp.lt.u32 q0, ex, %13;\n\t"                                                                        \
-    "setp.ne.or.u32 q0, %12, 0, q0;\n\t"                                                                  \
-    "vote.sync.any.pred q1, q0, 0xffffffff;\n\t"                                                          \
-    "@q1 bra.uni " G ";\n\t"
-
-#define ALACGPU_ENTROPY_FAST                                                                              \
-    "setp.eq.u32 pesc, ex, 0;\n\t"                                                                        \
-    "sub.u32 x, 135, ex;\n\t"                                                                             \
-    "sub.u32 s0, %9, ex;\n\t"                                                                             \
-    "add.u32 s0, s0, 8;\n\t"                                                                              \
-    "add.u32 s1, s0, 1;\n\t"                                                                              \
-    "shf.l.wrap.b32 e, w, 0, s1;\n\t"                                                                     \
-    "and.b32 e, e, %10;\n\t"                                                                              \
-    "max.u32 em, e, 1;\n\t"                                                                               \
-    "setp.ge.u32 pbig, e, 2;\n\t"                                                                         \
-    "mad.lo.u32 rice, x, %11, %8;\n\t"                                                                    \
-    "add.u32 rice, rice, em;\n\t"                                                                         \
-    "shl.b32 rawv, w, 9;\n\t"                          /* the raw field behind nine 1 bits (:198-202) */  \
-    "shr.u32 rawv, rawv, %16;\n\t"                                                                        \
-    "add.u32 rawv, rawv, %8;\n\t"                                                                         \
-    "add.u32 rawv, rawv, 1;\n\t"                                                                          \
-    "selp.u32 dv, rawv, rice, pesc;\n\t"                                                                  \
-    "add.u32 ta, %3, s0;\n\t"                                                                             \
-    "@pbig add.u32 ta, ta, 1;\n\t"                                                                        \
-    "add.u32 tb, %3, %21;\n\t"                                                                            \
-    "selp.u32 t, tb, ta, pesc;\n\t"                                                                       \
-    "setp.lt.u32 pA, %5, %6;\n\t"                                                                         \
-    "@!pA mov.u32 t, %3;\n\t"                                                                             \
-    /* move the cursor (BitCursor::seek) */                                                              \
-    "setp.ge.u32 prf, t, 32;\n\t"                                                                         \
-    "and.b32 %3, t, 31;\n\t"                                                                              \
-    "selp.u32 sel, 0x0123, 0x7654, prf;\n\t"                                                              \
-    "selp.u32 %0, %1, %0, prf;\n\t"                                                                       \
-    "prmt.b32 %1, %2, %1, sel;\n\t"                                                                       \
-    "and.b32 wa, %4, 63;\n\t"                                                                             \
-    "shl.b32 wa, wa, 2;\n\t"                                                                              \
-    "add.u32 wa, wa, %14;\n\t"                                                                            \
-    "@prf ld.shared.u32 %2, [wa];\n\t"                                                                    \
-    "@prf add.u32 %4, %4, 1;\n\t"                                                                         \
-    /* the value (:225-226) and the history (:229) */                                                    \
-    "and.b32 t1, dv, 1;\n\t"                                                                              \
-    "neg.s32 t1, t1;\n\t"                                                                                 \
-    "shr.u32 t2, dv, 1;\n\t"                                                                              \
-    "xor.b32 t2, t2, t1;\n\t"                                                                             \
-    "mad.wide.u32 ad, %5, 4, %20;\n\t"                                                                    \
-    "@pA st.global.u32 [ad], t2;\n\t"                                                                     \
-    "mul.lo.u32 t3, %7, %15;\n\t"                                                                         \
-    "shr.s32 t3, t3, 9;\n\t"                                                                              \
-    "sub.s32 t3, %7, t3;\n\t"                                                                             \
-    "mad.lo.u32 hn, dv, %15, t3;\n\t"                                                                     \
-    "setp.gt.u32 pbv, dv, 0xFFFF;\n\t"                                                                    \
-    "selp.s32 hn, 0xFFFF, hn, pbv;\n\t"                                                                   \
-    "@pA add.u32 %5, %5, 1;\n\t"                                                                          \
-    "@pA mov.s32 %7, hn;\n\t"                                                                             \
-    "@pA mov.u32 %8, 0xFFFFFFFF;\n\t"                                                                     \
-    "setp.lt.and.s32 pT, hn, 128, pA;\n\t"             /* :231, and a negative history (signed compare) */ \
-    "setp.lt.and.u32 pT, %5, %6, pT;\n\t"                                                                 \
-    "@pT mov.u32 %12, 4;\n\t"                                                                             \
-    /* k of the next value symbol (:221-222) */                                                          \
-    "shr.s32 t5, hn, 9;\n\t"                                                                              \
-    "add.s32 fk, t5, 0x4B000003;\n\t"                                                                     \
-    "add.rn.f32 fk, fk, 0fCB000000;\n\t"                                                                  \
-    "shr.b32 t5, fk, 23;\n\t"                                                                             \
-    "min.u32 kkv, t5, %17;\n\t"                                                                           \
-    "@pA mov.u32 %9, kkv;\n\t"                                                                            \
-    "shf.l.wrap.b32 t8, 2, 2, %9;\n\t"                                                                    \
-    "sub.u32 %10, t8, 1;\n\t"                                                                             \
-    "mov.u32 %11, %10;\n\t"
-
-// in front of a general step: resolve a pending run length (or stop the lane), RW -> pR / pW
-#define ALACGPU_ENTROPY_PEND                                                                              \
-    "and.b32 t0, %12, 4;\n\t"                                                                             \
-    "setp.ne.u32 q0, t0, 0;\n\t"                                                                          \
-    "setp.lt.and.s32 pF, %7, 0, q0;\n\t"               /* negative history: the lane stops here */        \
-    "setp.ge.and.s32 q1, %7, 0, q0;\n\t"                                                                  \
-    "@pF mov.u32 %6, 0;\n\t"                                                                              \
-    "@pF mov.u32 %12, 0;\n\t"                                                                             \
-    "bfind.u32 t6, %7;\n\t"                                                                               \
-    "add.u32 t7, %7, 16;\n\t"                                                                             \
-    "shr.u32 t7, t7, 6;\n\t"                                                                              \
-    "sub.u32 t7, t7, t6;\n\t"                                                                             \
-    "add.u32 t7, t7, 134;\n\t"                                                                            \
-    "setp.eq.u32 pz, %7, 0;\n\t"                                                                          \
-    "selp.u32 t7, 143, t7, pz;\n\t"                                                                       \
-    "@q1 mov.u32 %9, t7;\n\t"                                                                             \
-    "shf.l.wrap.b32 t8, 2, 2, %9;\n\t"                                                                    \
-    "sub.u32 t8, t8, 1;\n\t"                                                                              \
-    "and.b32 t9, t8, %18;\n\t"                                                                            \
-    "@q1 mov.u32 %10, t8;\n\t"                                                                            \
-    "@q1 mov.u32 %11, t9;\n\t"                                                                            \
-    "@q1 mov.s32 %7, 0;\n\t"                                                                              \
-    "@q1 mov.u32 %12, 1;\n\t"                                                                             \
-    "and.b32 t0, %12, 1;\n\t"                                                                             \
-    "setp.ne.u32 pR, t0, 0;\n\t"                                                                          \
-    "and.b32 t0, %12, 2;\n\t"                                                                             \
-    "setp.ne.u32 pW, t0, 0;\n\t"
-
-// behind a general step: pR / pW -> RW
-#define ALACGPU_ENTROPY_KIND_OUT                                                                          \
-    "selp.u32 t0, 1, 0, pR;\n\t"                                                                          \
-    "selp.u32 t1, 2, 0, pW;\n\t"                                                                          \
-    "or.b32 %12, t0, t1;\n\t"
-
-#define ALACGPU_ENTROPY_GENERAL(G) G ":\n\t" ALACGPU_ENTROPY_PEND ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_KIND_OUT
-
 // One block of 128 threads = 4 entropy warps.  `block` is the index among the entropy blocks;
 // ring_smem: kRingBytes * kK1Threads bytes, 256-byte aligned.  The planes must be zero on entry.
 template <bool kPublish>
@@ -470,10 +340,7 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
     uint32_t kk = kk0;                       // k + 127
     uint32_t mk = (1u << (kk - 127u)) - 1u;  // mask of the k-bit field
     uint32_t mm = mk;                        // multiplier of the unary part (:206; & kmask for a run length, :236)
-    uint32_t RW = 0;                         // kind of the field at the cursor: bit 0 a zero-run length (:234-236), bit 1 a raw
-                                             // field; bit 2: a run length whose k is still to be derived from h
-    const uint32_t exlim = d.rss > 23 ? 1u : 0u;   // 1: nine 1 bits + the raw field do not fit one window (general path)
-    const uint32_t esc_adv = 9u + (uint32_t)d.rss;
+    uint32_t R = 0, W = 0;                   // the field at the cursor is a zero-run length (:234-236) / a raw field
     uint8_t status = FS_OK;
 
     for (uint32_t period = 0;; ++period) {
@@ -509,44 +376,31 @@ __device__ __forceinline__ void entropy_block(const ChunkArgs &a, const int lane
                     kk = kk0;
                     mk = (1u << (kk - 127u)) - 1u;
                     mm = mk;
-                    RW = 0;
+                    R = W = 0;
                 }
             }
         }
         if (!__any_sync(0xffffffffu, chans != 0u)) break;
 
-        // kPeriod steps: the loop itself is inside the asm block so that the general steps sit behind it
-        static_assert(kPeriod % 4 == 0, "four steps per group");
-        asm volatile(
-            "{\n\t"
-            ".reg .pred pR, pW, pA, nA, pesc, pbig, palt, prf, pP, nP, nW, nR, pV, pU, pT, pF, pbv, pz, q0, q1;\n\t"
-            ".reg .b32 w, t0, fx, ex, x, s0, s1, e, em, rice, rsh, rawv, dv, alt, tb, ta, t, sel, wa;\n\t"
-            ".reg .b32 t1, t2, t3, hn, isum, t4, t5, fk, kkv, t6, t7, kn, t8, t9, grp;\n\t"
-            ".reg .b64 ad;\n\t"
-            "mov.u32 grp, %22;\n\t"
-            "EGLOOP:\n\t"
-            ALACGPU_ENTROPY_LOOK("EG1") ALACGPU_ENTROPY_FAST
-            ALACGPU_ENTROPY_LOOK("EG2") ALACGPU_ENTROPY_FAST
-            ALACGPU_ENTROPY_LOOK("EG3") ALACGPU_ENTROPY_FAST
-            ALACGPU_ENTROPY_LOOK("EG4") ALACGPU_ENTROPY_FAST
-            "add.u32 grp, grp, -1;\n\t"
-            "setp.ne.u32 q0, grp, 0;\n\t"
-            "@q0 bra.uni EGLOOP;\n\t"
-            "bra.uni EGEND;\n\t"
-            ALACGPU_ENTROPY_GENERAL("EG1")
-            ALACGPU_ENTROPY_GENERAL("EG2")
-            ALACGPU_ENTROPY_GENERAL("EG3")
-            ALACGPU_ENTROPY_GENERAL("EG4")
-            "add.u32 grp, grp, -1;\n\t"      /* (its own copy of the loop end: the common path keeps a single taken branch) */
-            "setp.ne.u32 q0, grp, 0;\n\t"
-            "@q0 bra.uni EGLOOP;\n\t"
-            "EGEND:\n\t"
-            "}"
-            : "+r"(br.cur), "+r"(br.nxt), "+r"(br.nn), "+r"(br.off), "+r"(br.wpos), "+r"(i), "+r"(nc), "+r"(h),
-              "+r"(smm1), "+r"(kk), "+r"(mk), "+r"(mm), "+r"(RW)
-            : "r"(exlim), "r"(br.ring), "r"(mult), "r"(rssh), "r"(kcap), "r"(kmask), "r"(kk_after_run), "l"(row),
-              "r"(esc_adv), "n"(kPeriod / 4)
-            : "memory");
+#pragma unroll 1
+        for (int u = 0; u < kPeriod; u += 4) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred pR, pW, pA, nA, pesc, pbig, palt, prf, pP, nP, nW, nR, pV, pU, pT, pF, pbv, pz, q0, q1;\n\t"
+                ".reg .b32 w, t0, fx, ex, x, s0, s1, e, em, rice, rsh, rawv, dv, alt, tb, ta, t, sel, wa;\n\t"
+                ".reg .b32 t1, t2, t3, hn, isum, t4, t5, fk, kkv, t6, t7, kn, t8, t9;\n\t"
+                ".reg .b64 ad;\n\t"
+                "setp.ne.u32 pR, %12, 0;\n\t"
+                "setp.ne.u32 pW, %13, 0;\n\t"
+                ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_STEP ALACGPU_ENTROPY_STEP
+                "selp.u32 %12, 1, 0, pR;\n\t"
+                "selp.u32 %13, 1, 0, pW;\n\t"
+                "}"
+                : "+r"(br.cur), "+r"(br.nxt), "+r"(br.nn), "+r"(br.off), "+r"(br.wpos), "+r"(i), "+r"(nc), "+r"(h),
+                  "+r"(smm1), "+r"(kk), "+r"(mk), "+r"(mm), "+r"(R), "+r"(W)
+                : "r"(br.ring), "r"(mult), "r"(rssh), "r"(kcap), "r"(kmask), "r"(kk_after_run), "l"(row)
+                : "memory");
+        }
     }
     cp_async_wait<0>();            // nothing may land in the ring after this block's shared memory is reused
     if (work) {

@@ -263,14 +263,20 @@ __device__ __noinline__ bool lpc_delta(int32_t *row, const int n, const int nmax
 // Steps are clamped to 2^25 > max |error| (|e| <= 2^24 for rss <= 25), so the sums cannot wrap and a
 // clamped step still ends the loop.  Surplus taps (j >= order) carry weight 0, coefficient 0 and an
 // unreachable threshold, so they contribute nothing and never update.
-template <int T, bool kPoll, bool kPublish>
-__device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax, const int rss, const int ord,
+//
+// L = 8 lanes per stream (four streams per warp, T*8 >= order) is the same code with one more level in the scan
+// and in the sum: for a batch so small that every warp has a scheduler to itself, a warp's time per sample
+// is its instruction count (one instruction per two cycles), and half the taps per lane is ~40 % fewer
+// instructions (`use_quads` bit 16, chosen per chunk by the runtime).
+template <int L, int T, bool kPoll, bool kPublish>
+__device__ __noinline__ bool lpc_lanes(int32_t *row, const int n, const int nmax, const int rss, const int ord,
                                        const int q, const int16_t *__restrict__ coef16, const bool active,
-                                       int32_t *ring /* this quad's column of a [32][8] shared ring */,
+                                       int32_t *ring /* this stream's column of a [32][8] shared ring */,
                                        const uint32_t *prog, uint32_t *done)
 {
+    static_assert(L == 4 || L == 8, "four or eight lanes per stream");
     const int lane = threadIdx.x & 31;
-    const int r4 = lane & 3;
+    const int r4 = lane & (L - 1);
     constexpr int32_t kClamp = 1 << 25;
     int32_t c[T], H[T], wgt[T], thr[T];
 #pragma unroll
@@ -300,8 +306,12 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
     for (int b = 0; b < nblk_max; b++) {
         if (kPoll && (b & 7) == 7) wait_avail(prog, (uint32_t)min(nblk, b + 11) * 4u, avail, active, stalled);
         const int4 nx2 = (active && b + 2 < nblk) ? __ldcg(row4 + b + 2) : make_int4(0, 0, 0, 0);
-        int32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-#pragma unroll 1
+        // The block's four samples are unrolled (unlike lpc_warp's: a quad lane has at most 8 taps, so four
+        // copies of the body still fit the instruction cache): no selects on the block's residuals / outputs,
+        // and the history shift turns into register renaming.  A lone warp issues one instruction per two
+        // cycles, and these streams are the critical path of a small batch.
+        int32_t ob[4] = {0, 0, 0, 0};
+#pragma unroll
         for (int u = 0; u < 4; u++) {
             const int i = b * 4 + u;
             const int32_t e = u == 0 ? cur.x : (u == 1 ? cur.y : (u == 2 ? cur.z : cur.w));
@@ -325,12 +335,17 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
                     st[t] = (int32_t)min((mag >> q) * (uint32_t)wgt[t], (uint32_t)kClamp);
                     mine += st[t];
                 }
-                // steps taken before this lane's first tap: the totals of the quad's HIGHER lanes
-                const int32_t t1 = __shfl_down_sync(0xffffffffu, mine, 1, 4);
-                const int32_t a1 = mine + (r4 < 3 ? t1 : 0);
-                const int32_t t2 = __shfl_down_sync(0xffffffffu, a1, 2, 4);
+                // steps taken before this lane's first tap: the totals of the group's HIGHER lanes
+                const int32_t t1 = __shfl_down_sync(0xffffffffu, mine, 1, L);
+                const int32_t a1 = mine + (r4 < L - 1 ? t1 : 0);
+                const int32_t t2 = __shfl_down_sync(0xffffffffu, a1, 2, L);
+                int32_t incl = a1 + (r4 < L - 2 ? t2 : 0);
+                if (L == 8) {
+                    const int32_t t4 = __shfl_down_sync(0xffffffffu, incl, 4, L);
+                    incl += r4 < 4 ? t4 : 0;
+                }
                 // (warm-up samples read a base that is not there yet: their steps are garbage, never used)
-                int32_t rem = main ? E0 - (a1 + (r4 < 2 ? t2 : 0) - mine) : -1;
+                int32_t rem = main ? E0 - (incl - mine) : -1;
                 // pass 2: sign-LMS update of the taps the reference's loop would have reached
 #pragma unroll
                 for (int t = T - 1; t >= 0; --t) {
@@ -338,8 +353,9 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
                     c[t] -= rem > thr[t] ? sg : 0;
                     rem -= st[t];
                 }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1, 4);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1, L);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2, L);
+                if (L == 8) acc += __shfl_xor_sync(0xffffffffu, acc, 4, L);
                 const int32_t sum = (int32_t)(acc * (uint32_t)nsg);         // sum of (buf[b+order-j]-buf[b])*coef[j]
                 int32_t v = (int32_t)((uint32_t)rnd + (uint32_t)sum) >> q;  // :306-307
                 v = (int32_t)((uint32_t)v + (uint32_t)base + (uint32_t)e);  // :308
@@ -347,7 +363,7 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
                 const int32_t x = main ? v : w;
                 o = (int32_t)((uint32_t)x << sh) >> sh;                     // :309-310
                 // history: every lane shifts by one tap; lane r takes lane r-1's oldest value
-                const int32_t from_below = __shfl_up_sync(0xffffffffu, H[T - 1], 1, 4);
+                const int32_t from_below = __shfl_up_sync(0xffffffffu, H[T - 1], 1, L);
 #pragma unroll
                 for (int t = T - 1; t > 0; --t) H[t] = H[t - 1];
                 H[0] = r4 == 0 ? o : from_below;
@@ -355,9 +371,9 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
                 __syncwarp();
                 prev = o;
             }
-            o0 = u == 0 ? o : o0; o1 = u == 1 ? o : o1; o2 = u == 2 ? o : o2; o3 = u == 3 ? o : o3;
+            ob[u] = o;
         }
-        if (active && r4 == 0 && b < nblk) row4[b] = make_int4(o0, o1, o2, o3);
+        if (active && r4 == 0 && b < nblk) row4[b] = make_int4(ob[0], ob[1], ob[2], ob[3]);
         if (kPublish && (b & 7) == 7) {              // hand-off to the pack warps, every 32 samples
             __threadfence();
             if (active && r4 == 0 && b < nblk) st_relaxed(done, (uint32_t)(b + 1) * 4u);
@@ -372,7 +388,7 @@ __device__ __noinline__ bool lpc_warp4(int32_t *row, const int n, const int nmax
     return stalled;
 }
 
-// One LPC warp.  The first ceil(n_quad / 8) warps take the four-lane streams (eight per warp), the
+// One LPC warp.  The first warps take the four-lane (eight-lane) streams, eight (four) per warp, the
 // others 32 one-lane streams of ONE order each.  hist_warp: this warp's 4 KB of shared memory (the
 // four-lane warps' output rings).
 template <bool kPoll, bool kPublish>
@@ -380,10 +396,13 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
 {
     const int lane = threadIdx.x & 31;
     const uint32_t n_active = a.perm_count[0], n_quad = a.perm_count[1];
-    const uint32_t quad_warps = (n_quad + 7u) / 8u;
+    const bool wide = (a.use_quads >> 16) & 1;                  // eight lanes per stream instead of four
+    const uint32_t per_warp = wide ? 4u : 8u;                    // multi-lane streams of one warp
+    const uint32_t quad_warps = (n_quad + per_warp - 1u) / per_warp;
     const bool quad = warp < quad_warps;
     if (!quad) warp -= quad_warps;
-    const uint32_t idx = quad ? warp * 8u + (uint32_t)(lane >> 2) : warp * 32u + (uint32_t)lane;
+    const uint32_t group = wide ? (uint32_t)(lane >> 3) : (uint32_t)(lane >> 2);
+    const uint32_t idx = quad ? warp * per_warp + group : warp * 32u + (uint32_t)lane;
     if (!quad && warp * 32u >= n_active) return;
     uint32_t sid = kNoStream;
     if (quad ? idx < n_quad : idx < n_active) sid = quad ? a.perm[quad_base(a.n) + idx] : a.perm[idx];
@@ -413,18 +432,23 @@ __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int3
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     bool stalled = false;
     if (quad) {
-        int32_t *ring = hist_warp + (lane >> 2);
+        int32_t *ring = hist_warp + group;
         if (!active) ord = 1;
-#define ALACGPU_LPC4(TT) stalled = lpc_warp4<TT, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, ring, prog, done)
-        if (maxo <= 8) ALACGPU_LPC4(2);
-        else if (maxo <= 12) ALACGPU_LPC4(3);
-        else if (maxo <= 16) ALACGPU_LPC4(4);
-        else if (maxo <= 20) ALACGPU_LPC4(5);
-        else if (maxo <= 24) ALACGPU_LPC4(6);
-        else if (maxo <= 28) ALACGPU_LPC4(7);
-        else ALACGPU_LPC4(8);
-#undef ALACGPU_LPC4
-        if (kPoll && active && stalled && (lane & 3) == 0) { a.desc[f].status = FS_INTERNAL; atomicAdd(a.faults, 1u); }
+#define ALACGPU_LPCL(LL, TT) stalled = lpc_lanes<LL, TT, kPoll, kPublish>(row, n, nmax, rss, ord, q, coef16, active, ring, prog, done)
+        if (wide) {
+            if (maxo <= 8) ALACGPU_LPCL(8, 1);
+            else if (maxo <= 16) ALACGPU_LPCL(8, 2);
+            else if (maxo <= 24) ALACGPU_LPCL(8, 3);
+            else ALACGPU_LPCL(8, 4);
+        } else if (maxo <= 8) ALACGPU_LPCL(4, 2);
+        else if (maxo <= 12) ALACGPU_LPCL(4, 3);
+        else if (maxo <= 16) ALACGPU_LPCL(4, 4);
+        else if (maxo <= 20) ALACGPU_LPCL(4, 5);
+        else if (maxo <= 24) ALACGPU_LPCL(4, 6);
+        else if (maxo <= 28) ALACGPU_LPCL(4, 7);
+        else ALACGPU_LPCL(4, 8);
+#undef ALACGPU_LPCL
+        if (kPoll && active && stalled && (lane & (wide ? 7 : 3)) == 0) { a.desc[f].status = FS_INTERNAL; atomicAdd(a.faults, 1u); }
         return;
     }
 #define ALACGPU_LPC(MM) case MM: stalled = lpc_warp<MM, kPoll, kPublish>(row, n, nmax, rss, q, coef16, active, prog, done); break

@@ -49,6 +49,8 @@ constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
 constexpr int kSlots = 16;
 constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
+constexpr uint32_t kWideLpcMaxFrames = 1024;       // resident chunk up to here: eight LPC lanes per stream (issue_chunk)
+constexpr uint32_t kBothQuadMaxFrames = 2048;      // ... up to here: four-lane LPC on both channels' high orders
 // Frame-lane path (kf_frame.cu): one lane per frame and channel from bitstream to PCM.  A lane's task is 32
 // frames x 4096 samples (~5 ms), so the path needs MANY tasks per SM before its tails stop mattering: measured
 // on B200 (16-bit stereo, resident inputs) 46.6 vs 62.9 Gsamples/s for the stream-lane kernels at 174 k frames
@@ -511,18 +513,31 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.plane_bytes = (uint64_t)s.planes.cap * sizeof(int32_t);
     ca.pcm_bytes = pcm_override ? ctx->total_pcm : d.pcm_hi - d.pcm_lo + 64;
     {
-        // four-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
-        // streams from order 17 up (configs[1], final r1 kernels: 2.65 ms; from 25 up 2.61, from 21 up 3.24,
-        // from 13 up 3.00, none 2.86, both channels from 17 up 3.1 ms -- the extra warps slow the entropy
-        // lanes down, and which blocks end up sharing an SM matters as much as the threshold).  While chunks
+        // multi-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
+        // streams from order 17 up get four lanes (configs[1], final r1 kernels: 2.65 ms; from 25 up 2.61, from 21
+        // up 3.24, from 13 up 3.00, none 2.86, both channels from 17 up 3.1 ms -- the extra warps slow the entropy
+        // lanes down, and which blocks end up sharing an SM matters as much as the threshold).  A resident batch
+        // so small that every warp has a scheduler to itself (configs[0], [2]) is bound by ONE stream's chain,
+        // and a lone warp's time per sample is its instruction count: eight lanes per stream, both channels,
+        // from order 9 up (kWideLpcMaxFrames); up to kBothQuadMaxFrames the first channel's high orders get
+        // four lanes too (its order-30 one-lane chain is longer than the whole entropy stage).  While chunks
         // stream in from the host the GPU has slack and the first PCM should leave as early as possible:
         // both channels (end to end 9.9 -> 9.65 ms).
-        static const int q_last = getenv("ALACGPU_QUAD_MIN_LAST") ? atoi(getenv("ALACGPU_QUAD_MIN_LAST")) : 17;
+        static const int q_last = getenv("ALACGPU_QUAD_MIN_LAST") ? atoi(getenv("ALACGPU_QUAD_MIN_LAST")) : -1;
         static const int q_first = getenv("ALACGPU_QUAD_MIN_FIRST") ? atoi(getenv("ALACGPU_QUAD_MIN_FIRST")) : -1;
         static const int q_early = getenv("ALACGPU_QUAD_MIN_EARLY") ? atoi(getenv("ALACGPU_QUAD_MIN_EARLY")) : 0;
-        int ql = q_last, qf = q_first >= 0 ? q_first : (streaming ? 17 : 0);
+        static const int q_wide = getenv("ALACGPU_LPC_WIDE") ? atoi(getenv("ALACGPU_LPC_WIDE")) : -1;
+        static const uint32_t wide_max = getenv("ALACGPU_WIDE_MAX_FRAMES") ? (uint32_t)atoi(getenv("ALACGPU_WIDE_MAX_FRAMES")) : kWideLpcMaxFrames;
+        static const uint32_t both_max = getenv("ALACGPU_BOTH_MAX_FRAMES") ? (uint32_t)atoi(getenv("ALACGPU_BOTH_MAX_FRAMES")) : kBothQuadMaxFrames;
+        int ql = 17, qf = streaming ? 17 : 0, wide = 0;
+        if (!streaming && c.n <= wide_max) { ql = qf = 9; wide = 1; }
+        else if (!streaming && c.n <= both_max) qf = 17;
+        if (q_last >= 0) ql = q_last;
+        if (q_first >= 0) qf = q_first;
+        if (q_wide >= 0) wide = q_wide;
         if (early && q_early > 0) ql = qf = q_early;          // the first chunks of a streamed call run on an idle GPU
-        ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC)) ? ((ql & 255) | ((qf & 255) << 8)) : 0;
+        ca.use_quads = (c.n <= kFullFusionMaxFrames && !(ctx->opts.flags & ALACGPU_FLAG_NO_QUAD_LPC))
+                           ? ((ql & 255) | ((qf & 255) << 8) | (wide ? 1 << 16 : 0)) : 0;
     }
     const size_t cf2 = 2u * (size_t)d.chunk_frames;
     ca.progress = s.progress.p;

@@ -46,8 +46,7 @@ class _Window:
         return ((self.value & ((1 << have) - 1)) << (32 - have)) & U32 if have else 0
 
 
-def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_escape=False, lane_mode=False, consume=None,
-                     others_general=None):
+def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_escape=False, lane_mode=False, consume=None):
     """Drop-in for alac_model.rice_decode built from the kernel's step.  `mask` is the run-length
     multiplier mask (1 << kmod) - 1 the model passes for the zero-run symbol (AlacFile.cs:236).
 
@@ -55,13 +54,7 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
     a register (`have`, `e`) until the predictor of the same lane consumes it -- which happens only in rounds
     where every lane of the warp has one, modelled by `consume(round) -> bool` -- a lane holding a residual
     (or still owing zeros of a run) sits the step out, and a zero run becomes `pend` zero residuals handed out one per round (clipped to the
-    frame) while the symbol index jumps as before.
-
-    others_general: the stream-lane loop of k1_entropy.cuh as it is now -- every step first looks at the window
-    (ALACGPU_ENTROPY_LOOK) and the warp votes: when no lane is at a run-length symbol or a raw field the warp takes
-    ALACGPU_ENTROPY_FAST (one-step escape for raw fields of at most 23 bits, a run length only flagged as
-    pending), else ALACGPU_ENTROPY_PEND + the general step.  `others_general(step) -> bool` stands for the other
-    31 lanes of the warp forcing the general path."""
+    frame) while the symbol index jumps as before."""
     assert mask == (1 << kmod) - 1
     win = _Window(br)
     out = [0] * n                                   # the cleared plane row
@@ -73,9 +66,6 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
     mk = ((1 << (kk - 127)) - 1) & U32
     mm = mk
     run, raw = False, False
-    pending = False                                 # bit 2 of RW: run length flagged by a fast step
-    exlim = 1 if rss > 23 else 0
-    fast_steps = 0
     steps = 0
     have, pend, e_reg, j, rounds = False, 0, 0, 0, 0
     while i < nc or (lane_mode and (have or pend)):
@@ -95,44 +85,6 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
         w = win.peek()
         ex = _exp_of(((w >> 23) ^ 0x1FF) | 0x4B000000)
         esc = ex == 0
-        if others_general is not None:
-            lane_general = run or raw or pending or ex < exlim
-            if not (lane_general or others_general(steps)):
-                # ---- ALACGPU_ENTROPY_FAST (a value symbol, or nine 1 bits + a narrow raw field) ----
-                fast_steps += 1
-                x = (135 - ex) & U32
-                s0 = (kk - ex + 8) & U32
-                s1 = (s0 + 1) & U32
-                sh = s1 & 31
-                e = ((w >> (32 - sh)) if sh else 0) & mk
-                rice = (x * mm + smm1 + max(e, 1)) & U32
-                rawv = ((((w << 9) & U32) >> (rssh & 31)) + smm1 + 1) & U32
-                dv = rawv if esc else rice
-                cons = ((9 + rss) if esc else (s1 if e >= 2 else s0)) & U32
-                assert cons <= 32, "a step moves the cursor by at most one word"
-                win.pos += cons
-                hb = _s32(h - (_s32(h * mult) >> 9))
-                hn = 0xFFFF if dv > 0xFFFF else _s32(dv * mult + hb)
-                out[i] = _s32((dv >> 1) ^ (-(dv & 1) & U32))
-                i += 1
-                h, smm1 = hn, U32
-                if hn < 128 and i < nc:
-                    pending = True
-                kk = min(_exp_of(((hn >> 9) + 0x4B000003) & U32), kcap)
-                mk = ((1 << ((kk + 1) & 31)) - 1) & U32
-                mm = mk
-                continue
-            # ---- ALACGPU_ENTROPY_PEND ----
-            if pending:
-                pending = False
-                if h < 0:
-                    nc = 0
-                    raise M.Unmodelled("negative rice history")
-                kk = 143 if h == 0 else ((h + 16) >> 6) - (h.bit_length() - 1) + 134
-                mk = ((1 << ((kk + 1) & 31)) - 1) & U32
-                mm = mk & mask
-                h = 0
-                run = True
         x = (135 - ex) & U32
         s0 = (kk - ex + 8) & U32
         s1 = (s0 + 1) & U32
@@ -201,10 +153,7 @@ def step_rice_decode(br, n, rss, initial_history, kmod, mult, mask, one_step_esc
                 have = False
     if lane_mode:
         assert j == n and not have and not pend, "every residual was handed out exactly once"
-    if others_general is not None and h < 0:
-        raise M.Unmodelled("negative rice history")     # found at the channel hand-over: frame status 6
     br.pos = win.pos
-    step_rice_decode.last_fast_share = fast_steps / max(1, steps)
     return out
 
 
@@ -315,41 +264,3 @@ def test_frame_lane_variant_hands_out_every_residual_once(idx, gen, monkeypatch)
     for consume in (None, lambda r: pattern[r % 997] == 0):
         monkeypatch.setattr(M, "rice_decode", lambda *a: step_rice_decode(*a, lane_mode=True, consume=consume))
         assert M.decode_track(ck, t.mdat, t.stsz) == t.pcm
-
-
-@pytest.mark.parametrize("idx", range(len(CASES)))
-def test_fast_and_general_steps_mix(idx, gen, monkeypatch):
-    """k1_entropy.cuh: the warp-voted fast step (one-step narrow escape, pending run length) interleaved at
-    random with the general step decodes the same streams; alone (no other lane ever forcing the general path)
-    it carries most steps of ordinary material"""
-    ss, ch, kw = CASES[idx]
-    kw = dict(kw)
-    rng = np.random.default_rng(7000 + idx)
-    cfg = gen.TrackCfg(ss, ch, 256, kw.pop("hist_mult", 40), kw.pop("init_hist", 10), kw.pop("kmod", 14), 44100)
-    total = 256 * 4 + 55
-    x = gen.make_signal(int(rng.integers(1, 1 << 31)), total, ss, 44100, ch, wasted_spans=(ss == 24)).copy()
-    loud = kw.pop("loud", False)
-    if loud:
-        lim = 1 << (ss - 1)
-        x[:, ::3] = rng.integers(-lim, lim, size=x[:, ::3].shape)
-    quiet = kw.pop("quiet", False)
-    if quiet:
-        x[:] = 0
-        x[:, rng.integers(0, total, size=40)] = rng.integers(-3, 4, size=(ch, 40))
-    fr = gen.make_frames(rng, cfg, total, ch == 2, **kw)
-    if ss == 24:
-        gen.assign_wasted_bytes(fr, x, 24, rng)
-    t = gen.build_track(cfg, x, fr)
-    ck = M.Cookie(cfg.sample_size, cfg.num_channels, cfg.max_samples_per_frame, cfg.rice_history_mult,
-                  cfg.rice_initial_history, cfg.rice_kmodifier)
-    pattern = rng.integers(0, 4, size=1009)
-    shares = []
-    for others in (lambda st: False, lambda st: pattern[st % 1009] == 0, lambda st: pattern[st % 1009] != 0):
-        def dec(*a):
-            out = step_rice_decode(*a, others_general=others)
-            shares.append(step_rice_decode.last_fast_share)
-            return out
-        monkeypatch.setattr(M, "rice_decode", dec)
-        assert M.decode_track(ck, t.mdat, t.stsz) == t.pcm
-    if idx == 0:
-        assert shares and max(shares) > 0.9
