@@ -49,8 +49,8 @@ constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
 constexpr int kSlots = 16;
 constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
-constexpr uint32_t kWideLpcMaxFrames = 1024;       // resident chunk up to here: eight LPC lanes per stream (issue_chunk)
-constexpr uint32_t kBothQuadMaxFrames = 2048;      // ... up to here: four-lane LPC on both channels' high orders
+constexpr uint32_t kSmallBatchFrames = 4096;       // resident chunk up to here: multi-lane LPC on both channels from order 5 up (issue_chunk)
+constexpr uint32_t kWideLpcMaxFrames = 1536;       // ... mono tracks, up to here: eight lanes per stream instead of four
 // Frame-lane path (kf_frame.cu): one lane per frame and channel from bitstream to PCM.  A lane's task is 32
 // frames x 4096 samples (~5 ms), so the path needs MANY tasks per SM before its tails stop mattering: measured
 // on B200 (16-bit stereo, resident inputs) 46.6 vs 62.9 Gsamples/s for the stream-lane kernels at 174 k frames
@@ -202,6 +202,7 @@ struct alacgpu_ctx {
     uint64_t total_pcm = 0;
     uint64_t compressed_bytes = 0;
     uint32_t max_sf = 0;                  // most sample-frames any frame emits
+    bool mono_only = true;                // every track's container has one channel
     uint32_t index_launches = 0;
     alacgpu_timing timing{};
     // stage timings of the last pipeline are read back from its CUDA events on demand (alacgpu_get_timing):
@@ -513,25 +514,28 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
     ca.plane_bytes = (uint64_t)s.planes.cap * sizeof(int32_t);
     ca.pcm_bytes = pcm_override ? ctx->total_pcm : d.pcm_hi - d.pcm_lo + 64;
     {
-        // multi-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  Resident batch: the last channel's
-        // streams from order 17 up get four lanes (configs[1], final r1 kernels: 2.65 ms; from 25 up 2.61, from 21
-        // up 3.24, from 13 up 3.00, none 2.86, both channels from 17 up 3.1 ms -- the extra warps slow the entropy
-        // lanes down, and which blocks end up sharing an SM matters as much as the threshold).  A resident batch
-        // so small that every warp has a scheduler to itself (configs[0], [2]) is bound by ONE stream's chain,
-        // and a lone warp's time per sample is its instruction count: eight lanes per stream, both channels,
-        // from order 9 up (kWideLpcMaxFrames); up to kBothQuadMaxFrames the first channel's high orders get
-        // four lanes too (its order-30 one-lane chain is longer than the whole entropy stage).  While chunks
-        // stream in from the host the GPU has slack and the first PCM should leave as early as possible:
-        // both channels (end to end 9.9 -> 9.65 ms).
+        // multi-lane LPC (k2_lpc.cuh) for small, latency-bound chunks.  A mid-size resident batch (configs[1]):
+        // the last channel's streams from order 17 up get four lanes (final r1 kernels: 2.65 ms; from 25 up 2.61,
+        // from 21 up 3.24, from 13 up 3.00, none 2.86, both channels from 17 up 3.1 ms -- the extra warps slow the
+        // entropy lanes down, and which blocks end up sharing an SM matters as much as the threshold).  A SMALL
+        // resident batch (configs[0], [2]; up to kSmallBatchFrames) leaves most schedulers idle and is bound by
+        // ONE stream's chain -- a lone warp's time per sample is its instruction count -- so both channels get
+        // four lanes from order 5 up (r2 sweep, 16-bit stereo, 646 / 1,292 / 2,584 / 3,876 frames: 1.27 / 1.29 /
+        // 1.31 / 1.48 ms against 1.71 / 1.67 / 1.71 / ~1.72 with the mid-size rule; 10,336 frames: 2.41 with the
+        // mid-size rule, 2.58 / 2.74 with more lanes), and eight lanes when the tracks are mono and the batch is
+        // tiny (646 / 1,292 frames: 0.67 / 0.67 ms against 0.71 / 0.72 with four).  While chunks stream in from
+        // the host the GPU has slack and the first PCM should leave as early as possible: both channels from 17
+        // up (end to end 9.9 -> 9.65 ms).
         static const int q_last = getenv("ALACGPU_QUAD_MIN_LAST") ? atoi(getenv("ALACGPU_QUAD_MIN_LAST")) : -1;
         static const int q_first = getenv("ALACGPU_QUAD_MIN_FIRST") ? atoi(getenv("ALACGPU_QUAD_MIN_FIRST")) : -1;
         static const int q_early = getenv("ALACGPU_QUAD_MIN_EARLY") ? atoi(getenv("ALACGPU_QUAD_MIN_EARLY")) : 0;
         static const int q_wide = getenv("ALACGPU_LPC_WIDE") ? atoi(getenv("ALACGPU_LPC_WIDE")) : -1;
-        static const uint32_t wide_max = getenv("ALACGPU_WIDE_MAX_FRAMES") ? (uint32_t)atoi(getenv("ALACGPU_WIDE_MAX_FRAMES")) : kWideLpcMaxFrames;
-        static const uint32_t both_max = getenv("ALACGPU_BOTH_MAX_FRAMES") ? (uint32_t)atoi(getenv("ALACGPU_BOTH_MAX_FRAMES")) : kBothQuadMaxFrames;
+        static const uint32_t small_max = getenv("ALACGPU_SMALL_BATCH_FRAMES") ? (uint32_t)atoi(getenv("ALACGPU_SMALL_BATCH_FRAMES")) : kSmallBatchFrames;
         int ql = 17, qf = streaming ? 17 : 0, wide = 0;
-        if (!streaming && c.n <= wide_max) { ql = qf = 9; wide = 1; }
-        else if (!streaming && c.n <= both_max) qf = 17;
+        if (!streaming && c.n <= small_max) {
+            ql = qf = 5;
+            wide = ctx->mono_only && c.n <= kWideLpcMaxFrames;
+        }
         if (q_last >= 0) ql = q_last;
         if (q_first >= 0) qf = q_first;
         if (q_wide >= 0) wide = q_wide;
@@ -1187,6 +1191,7 @@ static int32_t add_track_impl(alacgpu_ctx *ctx, const alacgpu_track_cfg *cfg, co
                                                     "call alacgpu_clear_tracks first");
     HostTrack t{};
     t.cfg = *cfg;
+    if (cfg->num_channels != 1) ctx->mono_only = false;
     t.mdat = mdat;
     t.mdat_len = mdat_len;
     t.first_frame_offset = first_frame_offset;
@@ -1242,6 +1247,7 @@ int32_t alacgpu_clear_tracks(alacgpu_ctx *ctx)
     ctx->frame_off.clear();
     ctx->total_pcm = 0;
     ctx->max_sf = 0;
+    ctx->mono_only = true;
     invalidate(ctx);
     for (Device &d : ctx->devs) { d.f_lo = d.f_hi = 0; d.arena_staged = 0; }
     return ALACGPU_OK;

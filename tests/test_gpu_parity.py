@@ -368,7 +368,7 @@ def test_two_devices_in_one_context(gen, oracle):
 @pytest.mark.parametrize("env", [
     {"ALACGPU_QUAD_MIN_LAST": "3", "ALACGPU_QUAD_MIN_FIRST": "3", "ALACGPU_LPC_WIDE": "0"},   # four-lane LPC for (almost) every stream: T = 2..8
     {"ALACGPU_QUAD_MIN_LAST": "2", "ALACGPU_QUAD_MIN_FIRST": "2", "ALACGPU_LPC_WIDE": "1"},   # eight lanes per stream: T = 1..4
-    {"ALACGPU_WIDE_MAX_FRAMES": "0", "ALACGPU_BOTH_MAX_FRAMES": "0"},    # the large-chunk thresholds on small inputs
+    {"ALACGPU_SMALL_BATCH_FRAMES": "0"},                               # the mid-size thresholds on small inputs
     {"ALACGPU_QUAD_MIN_LAST": "9", "ALACGPU_QUAD_MIN_FIRST": "13"},
     {"ALACGPU_QUAD_MIN_LAST": "0", "ALACGPU_QUAD_MIN_FIRST": "0", "ALACGPU_NO_TAPER": "1"},   # one lane per stream only
     {"ALACGPU_TEST_INJECT_INTERNAL": "1"},      # pretend a fused hand-off timed out: the batch is decoded again unfused
