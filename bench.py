@@ -475,6 +475,8 @@ def latency_leg(name, args, local):
     return {"workload": corpus.desc, "frames": t.n_frames, "samples": t.n_samples,
             "device_ms": dev, "wall_ms": wall, "value": t.n_samples / (wall * 1e-3) / 1e6,
             "e2e_ms": e2e, "e2e_value": t.n_samples / (e2e * 1e-3) / 1e6, "unit": UNIT,
+            # integer-issue accounting of the fused entropy + LPC launch from the committed ncu capture of this config
+            "issue": load_profile_json("issue.json").get(name, {}).get("k12_entropy_lpc"),
             "parity": "bit-exact vs the encoder's input + device checksum"}
 
 
