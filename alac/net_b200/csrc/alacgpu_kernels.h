@@ -45,9 +45,9 @@ struct ChunkArgs {
     uint32_t n;
     uint32_t ns;                   // plane row stride in samples (multiple of 32)
     uint32_t max_sf;               // most sample-frames any frame of the batch emits
-    uint32_t *perm;                // K2 work lists, heaviest first: [0, 2n) one-lane streams, [2n, 4n) four-lane streams
-    uint32_t *perm_count;          // [0] = one-lane streams, [1] = four-lane streams
-    int use_quads;                 // small (latency-bound) chunk: streams that get four lanes each (thresholds, k2_lpc.cuh lpc_quad); 0 = none
+    uint32_t *perm;                // K2 work lists, heaviest first: [0, 2n) one-lane streams, [2n, 4n) multi-lane streams
+    uint32_t *perm_count;          // [0] = one-lane streams, [1] = multi-lane streams
+    int use_quads;                 // small (latency-bound) chunk: streams that get four lanes each (thresholds, k2_lpc.cuh lpc_quad; bit 16: eight lanes); 0 = none
     uint32_t *progress;            // fused launch: residuals published per stream by the entropy lanes (2n entries, zeroed before the launch)
     uint32_t *lpc_done;            // fused launch: predicted samples published per stream by the LPC lanes (2n entries, zeroed)
     uint32_t *pack_next;           // fused launch: next pack task (zeroed)

@@ -48,7 +48,7 @@ __device__ __forceinline__ int lpc_key(const FrameDesc &d, int ch)
 // Streams that set the batch's critical path when the chunk is small (fewer frames than lanes): the
 // LAST channel of a frame with a high predictor order.  Its residuals only start to appear once
 // the entropy lane has finished the other channel, and its order-30 recurrence is the slowest thing
-// in the pipeline, so these streams get FOUR lanes each (lpc_warp4) instead of one.  The rest of the
+// in the pipeline, so these streams get FOUR (or eight) lanes each (lpc_lanes) instead of one.  The rest of the
 // streams have slack and stay one lane per stream.
 // `use_quads` packs the two thresholds: bits 0..7 = smallest order that gets four lanes on the LAST
 // channel of a frame, bits 8..15 = the same for the other channel; 0 = never.
@@ -60,7 +60,7 @@ __device__ __forceinline__ bool lpc_quad(const FrameDesc &d, int ch, int key, in
 }
 
 // perm[0 .. n_rest): one-lane streams, heaviest order first, every order class padded with kNoStream to a
-// multiple of 32 (a warp never mixes orders); perm[quad_base(n) .. + n_quad): four-lane streams, heaviest
+// multiple of 32 (a warp never mixes orders); perm[quad_base(n) .. + n_quad): multi-lane streams, heaviest
 // first; perm_count[0] = n_rest (padded), perm_count[1] = n_quad.
 constexpr uint32_t kPermPad = 32u * 32u;            // room for the padding of the 31 one-lane classes
 __host__ __device__ __forceinline__ uint32_t quad_base(uint32_t n_frames) { return 2u * n_frames + kPermPad; }
@@ -254,7 +254,7 @@ __device__ __noinline__ bool lpc_delta(int32_t *row, const int n, const int nmax
     return stalled;
 }
 
-// ---- four lanes per stream ---------------------------------------------------------------------
+// ---- four (or eight) lanes per stream ---------------------------------------------------------------------
 // Lane r (0..3) of a quad owns taps j = r*T + t, t < T (T*4 >= order); eight streams per warp.  The
 // reference's early-exit loop over the taps (AlacFile.cs:322-331: newest coefficient index first, stop
 // when the running error changes sign) becomes a prefix problem: every tap's step
@@ -390,7 +390,7 @@ __device__ __noinline__ bool lpc_lanes(int32_t *row, const int n, const int nmax
 
 // One LPC warp.  The first warps take the four-lane (eight-lane) streams, eight (four) per warp, the
 // others 32 one-lane streams of ONE order each.  hist_warp: this warp's 4 KB of shared memory (the
-// four-lane warps' output rings).
+// multi-lane warps' output rings).
 template <bool kPoll, bool kPublish>
 __device__ __forceinline__ void lpc_role(const ChunkArgs &a, uint32_t warp, int32_t *hist_warp)
 {

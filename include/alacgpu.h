@@ -105,7 +105,7 @@ typedef struct alacgpu_ctx alacgpu_ctx;
 #define ALACGPU_FLAG_NO_FUSION 0x2u          /* entropy, LPC and pack as three kernels */
 #define ALACGPU_FLAG_NO_PACK_FUSION 0x4u     /* never the launch with pack roles: un-mix / pack stays a separate kernel */
 #define ALACGPU_FLAG_NO_ZERO_COPY 0x8u       /* never write PCM straight into a page-locked destination; always device PCM + D2H copies */
-#define ALACGPU_FLAG_NO_QUAD_LPC 0x10u       /* one lane per stream for every LPC stream (no four-lane path for the tail-critical ones) */
+#define ALACGPU_FLAG_NO_QUAD_LPC 0x10u       /* one lane per stream for every LPC stream (no multi-lane path for the tail-critical ones) */
 #define ALACGPU_FLAG_FORCE_PACK_FUSION 0x20u /* the launch with pack roles even when the PCM stays in HBM (tests / A-B runs) */
 #define ALACGPU_FLAG_NO_FRAME_LANES 0x40u    /* never the frame-lane kernels (one lane per frame and channel from bitstream to PCM), which big batches use by default */
 #define ALACGPU_FLAG_FORCE_FRAME_LANES 0x80u /* the frame-lane kernels for every chunk, however small (tests / A-B runs) */

@@ -1,8 +1,8 @@
-"""CPU: the four-lanes-per-stream formulation of the adaptive predictor (alac/net_b200/csrc/k2_lpc.cuh,
-lpc_warp4) restated in Python and checked against the independent model's PredictorDecompressFirAdapt.
+"""CPU: the several-lanes-per-stream formulation of the adaptive predictor (alac/net_b200/csrc/k2_lpc.cuh,
+lpc_lanes<L, T>, L = 4 or 8) restated in Python and checked against the independent model's PredictorDecompressFirAdapt.
 
 What it pins, without a GPU: the reference's early-exit loop over the taps (AlacFile.cs:322-331) as a
-suffix scan over unconditionally computed, clamped steps; taps split j = r*T + t over the four lanes;
+suffix scan over unconditionally computed, clamped steps; taps split j = r*T + t over the lanes;
 surplus taps (j >= order) with weight 0 and an unreachable threshold; warm-up samples reading a base that
 is not there yet (modelled as garbage) without touching the coefficients; 32-bit wraparound everywhere."""
 import random
@@ -88,7 +88,7 @@ def quad_predict(e, n, rss, coef, order, q, T, rng, L=4):
     return o
 
 
-def _taps_per_lane(order):          # lpc_role's choice of the lpc_warp4 instantiation
+def _taps_per_lane(order):          # lpc_role's choice of the lpc_lanes<4, T> instantiation
     for limit, T in ((8, 2), (12, 3), (16, 4), (20, 5), (24, 6), (28, 7)):
         if order <= limit:
             return T
@@ -116,7 +116,8 @@ def test_quad_formulation_equals_the_reference_loop(seed):
 
 @pytest.mark.parametrize("lanes", [2, 8])
 def test_other_lane_counts_use_the_same_scan(lanes):
-    """not in the kernels yet: two and eight lanes per stream are the same formulation"""
+    """eight lanes per stream (lpc_lanes<8, T>: tiny mono batches, T = ceil(order / 8) taps per lane) and two (not in
+    the kernels) are the same formulation"""
     rng = random.Random(100 + lanes)
     for _ in range(40):
         order = rng.randint(1, 30)
