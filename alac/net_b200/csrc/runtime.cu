@@ -49,7 +49,7 @@ constexpr uint64_t kArenaTail = 256 * 1024 + 256;
 constexpr uint32_t kMaxChunkFrames = 32768;
 constexpr int kSlots = 16;
 constexpr uint32_t kFullFusionMaxFrames = 20480;   // largest chunk decoded by the fully fused launch
-constexpr uint32_t kSmallBatchFrames = 4096;       // resident chunk up to here: multi-lane LPC on both channels from order 5 up (issue_chunk)
+constexpr uint32_t kSmallBatchFrames = 10240;      // resident chunk up to here: multi-lane LPC on both channels from order 5 up (issue_chunk)
 constexpr uint32_t kWideLpcMaxFrames = 1536;       // ... mono tracks, up to here: eight lanes per stream instead of four
 // Frame-lane path (kf_frame.cu): one lane per frame and channel from bitstream to PCM.  A lane's task is 32
 // frames x 4096 samples (~5 ms), so the path needs MANY tasks per SM before its tails stop mattering: measured
@@ -518,11 +518,12 @@ int32_t issue_chunk(alacgpu_ctx *ctx, Device &d, const Chunk &c, Slot &s, bool w
         // the last channel's streams from order 17 up get four lanes (final r1 kernels: 2.65 ms; from 25 up 2.61,
         // from 21 up 3.24, from 13 up 3.00, none 2.86, both channels from 17 up 3.1 ms -- the extra warps slow the
         // entropy lanes down, and which blocks end up sharing an SM matters as much as the threshold).  A SMALL
-        // resident batch (configs[0], [2]; up to kSmallBatchFrames) leaves most schedulers idle and is bound by
+        // resident batch (configs[0], [2]; up to kSmallBatchFrames) leaves schedulers idle and is bound by
         // ONE stream's chain -- a lone warp's time per sample is its instruction count -- so both channels get
-        // four lanes from order 5 up (r2 sweep, 16-bit stereo, 646 / 1,292 / 2,584 / 3,876 frames: 1.27 / 1.29 /
-        // 1.31 / 1.48 ms against 1.71 / 1.67 / 1.71 / ~1.72 with the mid-size rule; 10,336 frames: 2.41 with the
-        // mid-size rule, 2.58 / 2.74 with more lanes), and eight lanes when the tracks are mono and the batch is
+        // four lanes from order 5 up (r2 sweep, 16-bit stereo, 646 / 1,292 / 2,584 / 3,876 / 5,168 / 7,752 / 10,336
+        // frames: 1.27 / 1.29 / 1.31 / 1.48 / 1.74 / 2.09 / 2.32 ms against 1.71 / 1.67 / 1.71 / ~1.72 / 1.74 / 2.42 /
+        // 2.42 with the mid-size rule; 15,504 / 19,380 frames: 3.50 / 3.96 against 2.97 / 3.14; configs[1], 14,063
+        // frames of 24-bit material: 3.21 against 2.73), and eight lanes when the tracks are mono and the batch is
         // tiny (646 / 1,292 frames: 0.67 / 0.67 ms against 0.71 / 0.72 with four).  While chunks stream in from
         // the host the GPU has slack and the first PCM should leave as early as possible: both channels from 17
         // up (end to end 9.9 -> 9.65 ms).
